@@ -1,0 +1,72 @@
+"""CPU, build container only: oracle restatement vs the LIVE reference on larger
+and randomised inputs (skipped where /root/reference is absent, e.g. the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ea_oracle as orc
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+
+
+def _ref_csr(n_ent, KG):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        du = ref_shim.ref.data_utils
+        adj = du.sparse_mx_to_torch_sparse_tensor(du.get_sparse_tensor(n_ent, KG))
+        csr = adj.coalesce().to_sparse_csr()
+    return csr.crow_indices().numpy(), csr.col_indices().numpy(), csr.values().numpy()
+
+
+@pytest.mark.parametrize("seed,n_ent,n_tri", [(0, 50, 0), (1, 1, 3), (2, 40, 300), (3, 500, 2500), (4, 2000, 9000)])
+def test_adjacency_random(seed, n_ent, n_tri, capsys):
+    rng = np.random.default_rng(seed)
+    h = rng.integers(0, n_ent, n_tri)
+    t = rng.integers(0, n_ent, n_tri)
+    if n_tri > 20:
+        t[:5] = h[:5]
+        h[5:10], t[5:10] = t[10:15], h[10:15]
+    KG = [(int(a), 0, int(b)) for a, b in zip(h, t)]
+    if n_tri == 0:
+        crow, col, val = orc.adjacency_csr(n_ent, h, t)
+        assert crow.tolist() == [0] * (n_ent + 1) and len(col) == 0
+        return
+    rc, cc, vc = _ref_csr(n_ent, KG)
+    crow, col, val = orc.adjacency_csr(n_ent, h, t)
+    assert np.array_equal(crow, rc) and np.array_equal(col, cc)
+    assert np.array_equal(val.view(np.uint32), vc.view(np.uint32))
+
+
+def test_adjacency_dbp15k_shape():
+    from gnn_mtl_b200.synth import make_kg_pair
+    kg = make_kg_pair("dbp15k", features=False)
+    tri = kg["triples"]
+    KG = [tuple(r) for r in tri.tolist()]
+    rc, cc, vc = _ref_csr(kg["n"], KG)
+    crow, col, val = orc.adjacency_csr(kg["n"], tri[:, 0], tri[:, 2])
+    assert np.array_equal(crow, rc) and np.array_equal(col, cc)
+    assert np.array_equal(val.view(np.uint32), vc.view(np.uint32))
+
+
+def test_sinkhorn_bsz300_reference_defaults():
+    torch.manual_seed(0)
+    X, Y = torch.randn(300, 32) * 0.1, torch.randn(300, 32) * 0.1
+    M = torch.cdist(X, Y)
+    a = b = torch.ones(300)
+    P0, l0 = ref_shim.ref.ot_loss.sinkhorn(a, b, M, 0.01, numItermax=120)
+    P1, l1 = orc.sinkhorn_scaling(a, b, M, 0.01, numItermax=120)
+    assert torch.allclose(P0, P1, rtol=1e-12, atol=0) and torch.allclose(l0, l1, rtol=1e-12)
+
+
+def test_hits_and_negatives_medium():
+    rng = np.random.default_rng(5)
+    vec = torch.from_numpy(rng.standard_normal((700, 24)).astype(np.float32))
+    pairs = np.stack([rng.permutation(350)[:200], rng.permutation(350)[:200] + 350], 1)
+    assert ref_shim.ref.eval_utils.get_hits(vec, pairs) == orc.get_hits(vec, pairs)
+
+    class _A:
+        n_nodes, device = 700, "cpu"
+    neg = ref_shim.ref.models_ea.BaseModel(_A()).get_neg(pairs[:50, 0], vec, 25)
+    assert np.array_equal(neg, orc.nearest_negatives(pairs[:50, 0], vec, 25))
