@@ -1,0 +1,173 @@
+"""GCN / highway-GCN layers on the eagraft SpMM kernels.
+
+Same class names, constructor signatures, attribute names and state_dict keys as
+the reference's layers/layers.py (GraphConvolution :19-42, HighWayGraphConvolution
+:45-80, Linear :83-96, get_dim_act :8-16), so models/encoders.py-style glue works
+unchanged.  What differs is the execution: the sparse aggregation, activation and
+highway blend run as ONE CUDA kernel (eg_spmm), and the backward is a fused
+element-wise kernel followed by the same SpMM on the transposed CSR.  The two
+small dense GEMMs per layer (x·Wᵀ + b and x·G + c) stay on cuBLAS through PyTorch
+(SURVEY.md §2.1 K1/K5).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.modules.module import Module
+
+from .. import _lib, ops
+from ..adjacency import resolve
+
+
+def get_dim_act(args):
+    """layers/layers.py:8-16: (num_layers-1) layers, dims [feat_dim] + [dim]*(L-1)."""
+    act = (lambda x: x) if not args.act else getattr(F, args.act)
+    n = args.num_layers - 1
+    return [args.feat_dim] + [args.dim] * n, [act] * n
+
+
+def classify_activation(act):
+    """Map the callable the reference passes around to a fused-epilogue code.
+    Returns ACT_IDENTITY / ACT_RELU, or None for anything else (un-fused path)."""
+    if act is None:
+        return _lib.ACT_IDENTITY
+    if act in (F.relu, torch.relu):
+        return _lib.ACT_RELU
+    probe = torch.tensor([-2.0, -0.5, 0.0, 0.75, 3.0])
+    try:
+        got = act(probe)
+    except Exception:
+        return None
+    if torch.equal(got, probe):
+        return _lib.ACT_IDENTITY
+    if torch.equal(got, torch.relu(probe)):
+        return _lib.ACT_RELU
+    return None
+
+
+class _Aggregate(torch.autograd.Function):
+    """out = epilogue(A · hidden);  backward: dH = Aᵀ · dS  (layers/layers.py:35,64 + autograd)."""
+
+    @staticmethod
+    def forward(ctx, hidden, gate_pre, x_res, adjacency, act_code):
+        needs_grad = any(ctx.needs_input_grad[:3])
+        save_act = needs_grad and (act_code == _lib.ACT_RELU or gate_pre is not None)
+        out, act_out = ops.spmm(adjacency.csr, hidden, act_code, gate_pre, x_res, save_act=save_act)
+        ctx.adjacency, ctx.act_code = adjacency, act_code
+        ctx.has_gate = gate_pre is not None
+        if ctx.has_gate:
+            ctx.save_for_backward(act_out, gate_pre, x_res)
+        else:
+            ctx.save_for_backward(act_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.has_gate:
+            act_out, gate_pre, x_res = ctx.saved_tensors
+        else:
+            (act_out,) = ctx.saved_tensors
+            gate_pre = x_res = None
+        need_h, need_g, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_gate = d_xres = None
+        if ctx.has_gate or ctx.act_code == _lib.ACT_RELU:
+            dS, d_gate, d_xres = ops.epilogue_bwd(dout, act_out, gate_pre, x_res, ctx.act_code, need_g, need_x)
+        else:
+            dS = dout
+        dH = None
+        if need_h:
+            dH, _ = ops.spmm(ctx.adjacency.csr_t, dS, _lib.ACT_IDENTITY)
+        return dH, d_gate, d_xres, None, None
+
+
+def _dense(x):
+    # the reference stores the (fully dense) feature matrix as sparse COO (utils/data_utils.py:358,397)
+    return x.to_dense() if x.is_sparse else x
+
+
+class GraphConvolution(Module):
+    """act(A · dropout(x Wᵀ + b)).  layers/layers.py:19-42."""
+
+    def __init__(self, in_features, out_features, dropout, act, use_bias):
+        super(GraphConvolution, self).__init__()
+        self.dropout = dropout
+        self.linear = nn.Linear(in_features, out_features, use_bias)
+        self.act = act
+        self.in_features = in_features
+        self.out_features = out_features
+        self._act_code = classify_activation(act)
+
+    def _aggregate(self, hidden, adj, gate_pre=None, x_res=None):
+        if torch.is_tensor(adj) and adj.layout == torch.strided:
+            # dense adjacency branch of the reference (:36-37); not the EA path
+            support = self.act(torch.mm(adj, hidden))
+            if gate_pre is None:
+                return support
+            t = torch.sigmoid(gate_pre)
+            return t * support + (1.0 - t) * x_res
+        adjacency = resolve(adj)
+        if self._act_code is None:
+            # activation the epilogue does not know: aggregate fused, activate/blend outside
+            support = self.act(_Aggregate.apply(hidden, None, None, adjacency, _lib.ACT_IDENTITY))
+            if gate_pre is None:
+                return support
+            t = torch.sigmoid(gate_pre)
+            return t * support + (1.0 - t) * x_res
+        return _Aggregate.apply(hidden, gate_pre, x_res, adjacency, self._act_code)
+
+    def forward(self, input):
+        x, adj = input
+        x = _dense(x)
+        hidden = self.linear.forward(x)
+        hidden = F.dropout(hidden, self.dropout, training=self.training)
+        return self._aggregate(hidden, adj), adj
+
+    def extra_repr(self):
+        return 'input_dim={}, output_dim={}'.format(self.in_features, self.out_features)
+
+
+class HighWayGraphConvolution(GraphConvolution):
+    """t·act(A·(xWᵀ+b)) + (1-t)·x with t = sigmoid(x G + c).  layers/layers.py:45-80.
+
+    kernel_gate / bias_gate are plain tensors as in the reference (not
+    Parameters, not in state_dict, moved by hand): initialised after nn.Linear
+    from the global RNG with U(±sqrt(6/2d)) / zeros (:51-54)."""
+
+    def __init__(self, in_features, out_features, dropout, act, use_bias, cuda, device):
+        super(HighWayGraphConvolution, self).__init__(in_features, out_features, dropout, act, use_bias)
+        assert (self.in_features == self.out_features)
+        d = self.in_features
+        init_range = np.sqrt(6.0 / (d + d))
+        self.kernel_gate = torch.FloatTensor(d, d).uniform_(-init_range, init_range)
+        self.bias_gate = torch.zeros([d])
+        if not cuda == -1:
+            self.kernel_gate = self.kernel_gate.to(device)
+            self.bias_gate = self.bias_gate.to(device)
+
+    def forward(self, input):
+        x, adj = input
+        x = _dense(x)
+        hidden = self.linear.forward(x)
+        hidden = F.dropout(hidden, self.dropout, training=self.training)
+        if self.kernel_gate.device != x.device:      # reference moves them in __init__ only
+            self.kernel_gate = self.kernel_gate.to(x.device)
+            self.bias_gate = self.bias_gate.to(x.device)
+        gate_pre = torch.addmm(self.bias_gate, x, self.kernel_gate)
+        return self._aggregate(hidden, adj, gate_pre, x), adj
+
+
+class Linear(Module):
+    """act(dropout(x Wᵀ + b)).  layers/layers.py:83-96 (dense; not a changed subsystem)."""
+
+    def __init__(self, in_features, out_features, dropout, act, use_bias):
+        super(Linear, self).__init__()
+        self.dropout = dropout
+        self.linear = nn.Linear(in_features, out_features, use_bias)
+        self.act = act
+
+    def forward(self, x):
+        hidden = self.linear.forward(x)
+        hidden = F.dropout(hidden, self.dropout, training=self.training)
+        return self.act(hidden)

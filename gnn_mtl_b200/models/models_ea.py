@@ -1,0 +1,145 @@
+"""Entity-alignment models: the callers of the hot path in models/models_ea.py
+(BaseModel.get_neg :19-30, compute_metrics :59-66, EAModel.get_loss :103-123,
+UEAModel.generate_pairs :143-167, generate_neg :169-183, get_loss_wassertein
+:206-224), keeping names, signatures and the reference's observable quirks.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..utils.eval_utils import get_hits
+from ..utils.ot_loss import sinkhorn
+from .decoders import model2decoder
+from .encoders import model2encoder
+
+
+class BaseModel(nn.Module):
+    def __init__(self, args):
+        super(BaseModel, self).__init__()
+        self.n_nodes = args.n_nodes
+        self.device = args.device
+
+    def get_neg(self, ILL, output, k):
+        """k nearest (L1, fp64) entities per anchor, rank 0 dropped; flat int64 [t*k]."""
+        out = output.detach().to(torch.float32)
+        anchors = torch.as_tensor(np.asarray(ILL, dtype=np.int64), device=out.device)
+        idx = ops.l1_topk(out.index_select(0, anchors), out, 1, k)
+        return idx.reshape(-1).cpu().numpy()
+
+    def compute_metrics(self, outputs, data, split):
+        pair = data['train'] if split == 'train' else data['test']
+        return get_hits(outputs, pair, top_k=[1])
+
+    def has_improved(self, m1, m2):
+        return (m1['Hits@10_l'] < m2['Hits@10_l']) or (m1['Hits@10_r'] < m2['Hits@10_r'])
+
+    def init_metric_dict(self):
+        return {'Hits@1_l': -1, 'Hits@10_l': -1, 'Hits@50_l': -1, 'Hits@100_l': -1,
+                'Hits@1_r': -1, 'Hits@10_r': -1, 'Hits@50_r': -1, 'Hits@100_r': -1}
+
+
+def _margin_loss(outputs, ILL, neg_left, neg_right, neg2_left, neg2_right, k):
+    """Margin-based L1 ranking loss with hard negatives (:103-123 / :185-204);
+    plain tensor algebra — SURVEY.md §8f rank 1, not a changed subsystem yet."""
+    t = len(ILL)
+    dev = outputs.device
+
+    def ix(a):
+        return torch.as_tensor(np.asarray(a, dtype=np.int64), device=dev)
+
+    A = torch.sum(torch.abs(outputs[ix(ILL[:, 0])] - outputs[ix(ILL[:, 1])]), 1)
+    D = A + 1.0
+    B = torch.sum(torch.abs(outputs[ix(neg_left)] - outputs[ix(neg_right)]), 1)
+    L1 = F.relu(torch.add(-torch.reshape(B, [t, k]), torch.reshape(D, [t, 1])))
+    B = torch.sum(torch.abs(outputs[ix(neg2_left)] - outputs[ix(neg2_right)]), 1)
+    L2 = F.relu(torch.add(-torch.reshape(B, [t, k]), torch.reshape(D, [t, 1])))
+    return (torch.sum(L1) + torch.sum(L2)) / (2.0 * t * k)
+
+
+class EAModel(BaseModel):
+    def __init__(self, args):
+        super(EAModel, self).__init__(args)
+        self.encoder = model2encoder[args.model](args)
+        self.decoder = model2decoder[args.model](args)
+        ILL = args.data['train']
+        t, k = len(ILL), args.neg_num
+        self.neg_num = k
+        self.neg_left = (np.ones((t, k)) * (ILL[:, 0].reshape((t, 1)))).reshape((t * k,))
+        self.neg2_right = (np.ones((t, k)) * (ILL[:, 1].reshape((t, 1)))).reshape((t * k,))
+        self.neg_right = None
+        self.neg2_left = None
+
+    def encode(self, x, adj):
+        return self.encoder.encode(x, adj)
+
+    def decode(self, h, adj):
+        return self.decoder.decode(h, adj)
+
+    def get_loss(self, outputs, data, split):
+        return _margin_loss(outputs, data[split], self.neg_left, self.neg_right, self.neg2_left,
+                            self.neg2_right, self.neg_num)
+
+
+class UEAModel(BaseModel):
+    def __init__(self, args):
+        super(UEAModel, self).__init__(args)
+        self.ILL = None
+        self.encoder = model2encoder[args.model](args)
+        self.decoder = model2decoder[args.model](args)
+
+    def encode(self, x, adj):
+        return self.encoder.encode(x, adj)
+
+    def decode(self, h, adj):
+        return self.decoder.decode(h, adj)
+
+    def generate_pairs(self, outputs, data, bsz):
+        """Mutual nearest neighbours under fp64 L1, closest first, at most bsz
+        (:143-167; positions are local, as in the reference)."""
+        e1, e2 = data['e1'], data['e2']
+        index1, index2 = data['index1'], data['index2']
+        out = outputs.detach().to(torch.float32)
+        L = torch.as_tensor([index1[i] for i in range(e1)], device=out.device)
+        R = torch.as_tensor([index2[i] for i in range(e2)], device=out.device)
+        row_min, row_arg, _, col_arg = ops.l1_argmins(out.index_select(0, L), out.index_select(0, R))
+        mutual = col_arg[row_arg] == torch.arange(e1, device=out.device)
+        keep = torch.nonzero(mutual).reshape(-1)
+        pairs = torch.stack([keep, row_arg[keep]], 1)
+        print("generate {} pairs by the L1 distance".format(min(len(pairs), bsz)))
+        order = torch.argsort(row_min[keep], stable=True)[:bsz]
+        self.ILL = pairs[order].cpu().numpy()
+        return
+
+    def generate_neg(self, outputs, k):
+        t = len(self.ILL)
+        self.neg_num = k
+        self.neg_left = (np.ones((t, k)) * (self.ILL[:, 0].reshape((t, 1)))).reshape((t * k,))
+        self.neg2_right = (np.ones((t, k)) * (self.ILL[:, 1].reshape((t, 1)))).reshape((t * k,))
+        self.neg_right = self.get_neg(self.ILL[:, 0], outputs, k)
+        self.neg2_left = self.get_neg(self.ILL[:, 1], outputs, k)
+        return
+
+    def get_loss(self, outputs):
+        return _margin_loss(outputs, self.ILL, self.neg_left, self.neg_right, self.neg2_left,
+                            self.neg2_right, self.neg_num)
+
+    def get_loss_wassertein(self, outputs, data, bsz, *, numItermax=1000, stopThr=1e-9):
+        """:206-224, quirk included: the Sinkhorn plan is computed and then not
+        used — the one-hot is taken from argmax of a zero tensor, i.e. column 0 —
+        so the value (and its gradient) is sum_i ||X_i - Y_0||_2."""
+        e1, e2 = data['e1'], data['e2']
+        index1, index2 = data['index1'], data['index2']
+        L = np.array([index1[i] for i in np.random.permutation(e1)[:bsz]])
+        R = np.array([index2[i] for i in np.random.permutation(e2)[:bsz]])
+        dev = outputs.device
+        X = outputs[torch.as_tensor(L, device=dev)]
+        Y = outputs[torch.as_tensor(R, device=dev)]
+        a, b = torch.ones(bsz, device=dev), torch.ones(bsz, device=dev)
+        M = torch.cdist(X, Y, p=2)
+        T, _ = sinkhorn(a, b, M.detach(), reg=0.01, numItermax=numItermax, stopThr=stopThr, return_plan=False)
+        # newT = one-hot(argmax(zeros)) = column 0 of every row (reference :221-222)
+        return torch.sum(M[:, 0].to(torch.float64))

@@ -1,0 +1,280 @@
+"""Thin tensor-level wrappers over the C ABI (allocation + argument marshalling).
+
+Everything here runs on CUDA tensors; nothing falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, ptr, stream, check
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+# ---- (a) SpMM ----------------------------------------------------------------
+
+def spmm(csr, H, act=_lib.ACT_IDENTITY, gate_pre=None, x_res=None, save_act=False):
+    """out = epilogue(csr · H); returns (out, act_out or None)."""
+    _lib.require_cuda(H, gate_pre, x_res)
+    H = _f32c(H)
+    n_rows, d = csr.n_rows, H.shape[1]
+    if H.shape[0] != csr.n_cols:
+        raise ValueError("spmm: H has %d rows, adjacency has %d columns" % (H.shape[0], csr.n_cols))
+    if gate_pre is not None:
+        gate_pre, x_res = _f32c(gate_pre), _f32c(x_res)
+    out = torch.empty(n_rows, d, dtype=torch.float32, device=H.device)
+    act_out = torch.empty_like(out) if save_act else None
+    with torch.cuda.device(H.device):
+        check(lib.eg_spmm(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), n_rows, ptr(H), d, act,
+                          ptr(gate_pre), ptr(x_res), ptr(out), ptr(act_out), csr.threshold,
+                          ptr(csr.seg_row), ptr(csr.seg_begin), ptr(csr.seg_end), csr.n_seg,
+                          ptr(csr.long_rows), ptr(csr.long_first), csr.n_long, ptr(csr.scratch(d)), stream()),
+              "eg_spmm")
+    return out, act_out
+
+
+def epilogue_bwd(dout, a, gate_pre, x_res, act, need_gate, need_xres):
+    dout = _f32c(dout)
+    dS = torch.empty_like(dout)
+    d_gate = torch.empty_like(dout) if (gate_pre is not None and need_gate) else None
+    d_xres = torch.empty_like(dout) if (gate_pre is not None and need_xres) else None
+    with torch.cuda.device(dout.device):
+        check(lib.eg_epilogue_bwd(ptr(dout), ptr(a), ptr(gate_pre), ptr(x_res), dout.numel(), act, ptr(dS),
+                                  ptr(d_gate), ptr(d_xres), stream()), "eg_epilogue_bwd")
+    return dS, d_gate, d_xres
+
+
+# ---- (c) L1 evaluation -----------------------------------------------------------
+
+L1_BLOCK_BYTES = 2 << 30   # fp64 distance rows materialised per launch
+
+
+def l1_block_rows(n_cols, budget=None):
+    rows = max(64, (budget or L1_BLOCK_BYTES) // (8 * max(int(n_cols), 1)))
+    return int(min(rows, 65535 * 32))
+
+
+def l1_matrix(L, R, out=None):
+    _lib.require_cuda(L, R)
+    L, R = _f32c(L), _f32c(R)
+    nL, d = L.shape
+    nR = R.shape[0]
+    if out is None:
+        out = torch.empty(nL, nR, dtype=torch.float64, device=L.device)
+    with torch.cuda.device(L.device):
+        check(lib.eg_l1_matrix(ptr(L), nL, ptr(R), nR, d, ptr(out), out.stride(0) if nL else nR, stream()),
+              "eg_l1_matrix")
+    return out
+
+
+def l1_paired(L, R):
+    L, R = _f32c(L), _f32c(R)
+    out = torch.empty(L.shape[0], dtype=torch.float64, device=L.device)
+    with torch.cuda.device(L.device):
+        check(lib.eg_l1_paired(ptr(L), ptr(R), L.shape[0], L.shape[1], ptr(out), stream()), "eg_l1_paired")
+    return out
+
+
+def rank_accumulate(D, row0, diag, rank_row, rank_col):
+    with torch.cuda.device(D.device):
+        check(lib.eg_rank_accumulate(ptr(D), D.stride(0), row0, D.shape[0], D.shape[1], ptr(diag), ptr(rank_row),
+                                     ptr(rank_col), stream()), "eg_rank_accumulate")
+
+
+def argmin_accumulate(D, row0, row_min, row_arg, col_min, col_arg):
+    with torch.cuda.device(D.device):
+        check(lib.eg_argmin_accumulate(ptr(D), D.stride(0), row0, D.shape[0], D.shape[1], ptr(row_min), ptr(row_arg),
+                                       ptr(col_min), ptr(col_arg), stream()), "eg_argmin_accumulate")
+
+
+def topk_rows(D, skip, k):
+    out = torch.empty(D.shape[0], k, dtype=torch.int64, device=D.device)
+    with torch.cuda.device(D.device):
+        check(lib.eg_topk_rows(ptr(D), D.stride(0), D.shape[0], D.shape[1], skip, k, ptr(out), stream()),
+              "eg_topk_rows")
+    return out
+
+
+def l1_ranks(L, R, block_bytes=None):
+    """Ranks of the diagonal (true match) per row and per column of the fp64 L1
+    matrix between L and R (same length)."""
+    n = L.shape[0]
+    dev = L.device
+    diag = l1_paired(L, R)
+    rank_row = torch.zeros(n, dtype=torch.int32, device=dev)
+    rank_col = torch.zeros(n, dtype=torch.int32, device=dev)
+    rows = l1_block_rows(n, block_bytes)
+    buf = torch.empty(min(rows, n), n, dtype=torch.float64, device=dev)
+    for r0 in range(0, n, rows):
+        r1 = min(n, r0 + rows)
+        D = l1_matrix(L[r0:r1], R, out=buf[: r1 - r0])
+        rank_accumulate(D, r0, diag, rank_row, rank_col)
+    return rank_row, rank_col
+
+
+def matrix_ranks(S):
+    """Same ranking on a given fp64 score matrix (square)."""
+    S = S.to(torch.float64).contiguous()
+    n = S.shape[0]
+    diag = torch.diagonal(S).contiguous()
+    rank_row = torch.zeros(n, dtype=torch.int32, device=S.device)
+    rank_col = torch.zeros(n, dtype=torch.int32, device=S.device)
+    step = 65535 * 32
+    for r0 in range(0, n, step):
+        rank_accumulate(S[r0:r0 + step], r0, diag, rank_row, rank_col)
+    return rank_row, rank_col
+
+
+def l1_argmins(L, R, block_bytes=None):
+    """(row_min, row_arg, col_min, col_arg) of the fp64 L1 matrix, lowest index on ties."""
+    nL, nR = L.shape[0], R.shape[0]
+    dev = L.device
+    row_min = torch.empty(nL, dtype=torch.float64, device=dev)
+    row_arg = torch.empty(nL, dtype=torch.int64, device=dev)
+    col_min = torch.full((nR,), float("inf"), dtype=torch.float64, device=dev)
+    col_arg = torch.full((nR,), -1, dtype=torch.int64, device=dev)
+    rows = l1_block_rows(nR, block_bytes)
+    buf = torch.empty(min(rows, max(nL, 1)), nR, dtype=torch.float64, device=dev)
+    for r0 in range(0, nL, rows):
+        r1 = min(nL, r0 + rows)
+        D = l1_matrix(L[r0:r1], R, out=buf[: r1 - r0])
+        argmin_accumulate(D, r0, row_min, row_arg, col_min, col_arg)
+    return row_min, row_arg, col_min, col_arg
+
+
+def l1_topk(L, R, skip, k, block_bytes=None):
+    nL, nR = L.shape[0], R.shape[0]
+    rows = l1_block_rows(nR, block_bytes)
+    buf = torch.empty(min(rows, max(nL, 1)), nR, dtype=torch.float64, device=L.device)
+    outs = []
+    for r0 in range(0, nL, rows):
+        r1 = min(nL, r0 + rows)
+        D = l1_matrix(L[r0:r1], R, out=buf[: r1 - r0])
+        outs.append(topk_rows(D, skip, k))
+    return torch.cat(outs) if outs else torch.empty(0, k, dtype=torch.int64, device=L.device)
+
+
+# ---- (b) Sinkhorn ------------------------------------------------------------------
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _lib.DT_F32
+    if t.dtype == torch.float64:
+        return _lib.DT_F64
+    raise TypeError("Sinkhorn kernels take fp32 or fp64, got %s" % t.dtype)
+
+
+def lse_dense(M, inv_reg, pot_in, logw=None, want_pot=True, want_lse=False):
+    """Row pass over a materialised cost: lse_i = LSE_j(pot_in_j - M_ij*inv_reg)."""
+    dt = _dt(M)
+    n_rows, n_cols = M.shape
+    pot_out = torch.empty(n_rows, dtype=M.dtype, device=M.device) if want_pot else None
+    lse_out = torch.empty(n_rows, dtype=M.dtype, device=M.device) if want_lse else None
+    with torch.cuda.device(M.device):
+        check(lib.eg_lse_dense(dt, ptr(M), n_rows, n_cols, M.stride(0), float(inv_reg), ptr(pot_in), ptr(logw),
+                               ptr(pot_out), ptr(lse_out), stream()), "eg_lse_dense")
+    return pot_out, lse_out
+
+
+def transpose(M):
+    out = torch.empty(M.shape[1], M.shape[0], dtype=M.dtype, device=M.device)
+    with torch.cuda.device(M.device):
+        check(lib.eg_transpose(_dt(M), ptr(M), M.shape[0], M.shape[1], M.stride(0), ptr(out), out.stride(0),
+                               stream()), "eg_transpose")
+    return out
+
+
+def plan_dense(M, inv_reg, f, g, want_plan=True, want_rows=False, want_cols=False):
+    dt = _dt(M)
+    I, J = M.shape
+    dev = M.device
+    P = torch.empty(I, J, dtype=M.dtype, device=dev) if want_plan else None
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    rs = torch.empty(I, dtype=M.dtype, device=dev) if want_rows else None
+    cs = torch.empty(J, dtype=M.dtype, device=dev) if want_cols else None
+    with torch.cuda.device(dev):
+        check(lib.eg_plan_dense(dt, ptr(M), I, J, M.stride(0), float(inv_reg), ptr(f), ptr(g), ptr(P),
+                                J, ptr(loss), ptr(rs), ptr(cs), stream()), "eg_plan_dense")
+    return P, loss[0], rs, cs
+
+
+def sinkhorn_dense(M, a, b, reg, max_iter, stop_thr):
+    """Device solver of utils/ot_loss.py:26-76; returns (log_u, log_v, sweeps, err)."""
+    dt = _dt(M)
+    I, J = M.shape
+    dev = M.device
+    Mt = torch.empty(J, I, dtype=M.dtype, device=dev)
+    log_u = torch.empty(I, dtype=M.dtype, device=dev)
+    log_v = torch.empty(J, dtype=M.dtype, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.eg_sinkhorn_dense_workspace_bytes(dt, I, J))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        sweeps, err = C.c_int(0), C.c_double(0.0)
+        check(lib.eg_sinkhorn_dense(dt, ptr(M), I, J, float(reg), ptr(a), ptr(b), int(max_iter), float(stop_thr),
+                                    ptr(Mt), ptr(log_u), ptr(log_v), ptr(ws), ws_bytes, C.byref(sweeps),
+                                    C.byref(err), stream()), "eg_sinkhorn_dense")
+    return log_u, log_v, int(sweeps.value), float(err.value)
+
+
+def row_norms(A, squared=True):
+    A = _f32c(A)
+    out = torch.empty(A.shape[0], dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.eg_row_norms(ptr(A), A.shape[0], A.shape[1], 1 if squared else 0, ptr(out), stream()),
+              "eg_row_norms")
+    return out
+
+
+def split_tf32(X, d_pad=None):
+    X = _f32c(X)
+    n, d = X.shape
+    d_pad = d_pad or (d + 7) // 8 * 8
+    hi = torch.empty(n, d_pad, dtype=torch.float32, device=X.device)
+    lo = torch.empty(n, d_pad, dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(lib.eg_split_tf32(ptr(X), n, d, d_pad, ptr(hi), ptr(lo), stream()), "eg_split_tf32")
+    return hi, lo
+
+
+class FusedOperand:
+    """One embedding set prepared for the fused passes: fp32 rows, norms for the
+    chosen cost, and (tcgen05 path) the 3xTF32 hi/lo split."""
+
+    def __init__(self, X, cost, algo):
+        self.X = _f32c(X)
+        self.n, self.d = self.X.shape
+        self.norm = row_norms(self.X, squared=(cost != _lib.COST_COSINE))
+        self.hi = self.lo = None
+        if algo == _lib.ALGO_TCGEN05:
+            self.hi, self.lo = split_tf32(self.X)
+
+
+def lse_fused(A, B, cost, inv_reg, pot_in, logw=None, algo=_lib.ALGO_SIMT, want_pot=True, want_lse=False):
+    """lse_i = LSE_j(pot_in_j - cost(A_i,B_j)*inv_reg) with A, B FusedOperand."""
+    dev = A.X.device
+    pot_out = torch.empty(A.n, dtype=torch.float32, device=dev) if want_pot else None
+    lse_out = torch.empty(A.n, dtype=torch.float32, device=dev) if want_lse else None
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.eg_lse_fused_workspace_bytes(algo, A.n, B.n, A.d))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        check(lib.eg_lse_fused(algo, cost, ptr(A.X), A.n, ptr(B.X), B.n, A.d, ptr(A.norm), ptr(B.norm),
+                               float(inv_reg), ptr(pot_in), ptr(logw), ptr(pot_out), ptr(lse_out),
+                               ptr(A.hi), ptr(A.lo), ptr(B.hi), ptr(B.lo), ptr(ws), ws.numel(), stream()),
+              "eg_lse_fused")
+    return pot_out, lse_out
+
+
+def plan_fused(A, B, cost, inv_reg, f, g, want_plan=False, want_rows=True):
+    dev = A.X.device
+    P = torch.empty(A.n, B.n, dtype=torch.float32, device=dev) if want_plan else None
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    rs = torch.empty(A.n, dtype=torch.float32, device=dev) if want_rows else None
+    with torch.cuda.device(dev):
+        check(lib.eg_plan_fused(cost, ptr(A.X), A.n, ptr(B.X), B.n, A.d, ptr(A.norm), ptr(B.norm), float(inv_reg),
+                                ptr(f), ptr(g), ptr(P), B.n, ptr(loss), ptr(rs), stream()), "eg_plan_fused")
+    return P, loss[0], rs

@@ -1,0 +1,193 @@
+/*
+ * eagraft — C ABI of the B200 (sm_100a) entity-alignment hot path.
+ *
+ * One shared library (gnn_mtl_b200/csrc/libeagraft.so), plain C linkage, raw
+ * device pointers + sizes + a cudaStream_t passed as void*.  No PyTorch types.
+ * The reference (HestiaSky/GNN-MTL) has no FFI of its own — its operator API is
+ * Python classes/functions — so each entry point below names the reference
+ * call site (file:line, relative to the reference checkout) whose work it takes
+ * over.  The Python host code in gnn_mtl_b200/ keeps the reference's names and
+ * signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - return 0 (EG_OK) or a negative eg_status; never throws, never exits;
+ *   - all pointers are DEVICE pointers unless the name starts with h_;
+ *   - work is enqueued on `stream` and is asynchronous unless stated;
+ *   - no hidden allocation: scratch comes from the caller (`ws`, `ws_bytes`),
+ *     sized by the matching *_workspace_bytes();
+ *   - pointers are borrowed for the duration of the enqueued work only;
+ *   - row-major, contiguous unless an ld* argument says otherwise.
+ */
+#ifndef EAGRAFT_H_
+#define EAGRAFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* eg_stream_t; /* cudaStream_t */
+
+enum eg_status {
+  EG_OK = 0,
+  EG_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unsupported d) */
+  EG_ERR_CUDA = -2,        /* a CUDA runtime call failed; see eg_last_cuda_error() */
+  EG_ERR_WORKSPACE = -3,   /* ws_bytes smaller than *_workspace_bytes() */
+  EG_ERR_UNSUPPORTED = -4, /* valid request this build cannot serve (e.g. k too large) */
+  EG_ERR_NO_DEVICE = -5    /* no sm_100 device visible */
+};
+
+enum eg_act { EG_ACT_IDENTITY = 0, EG_ACT_RELU = 1 };
+enum eg_cost { EG_COST_L2 = 0, EG_COST_SQEUCLID = 1, EG_COST_COSINE = 2 };
+enum eg_algo { EG_ALGO_SIMT = 0, EG_ALGO_TCGEN05 = 1 };
+
+/* ---- library ---------------------------------------------------------------- */
+int eg_version(void);
+const char* eg_strerror(int status);
+int eg_last_cuda_error(void);          /* cudaError_t of the last failure on this thread */
+int eg_device_check(void);             /* EG_OK iff current device is compute capability 10.x */
+int64_t eg_launch_count(void);         /* kernels launched by this library since reset */
+void eg_launch_count_reset(void);
+
+/* ---- (A) adjacency: triples -> degree-normalised CSR -------------------------
+ * Replaces utils/data_utils.py:296-336 (get_matrix, get_sparse_tensor) and the
+ * fp64->fp32 cast of sparse_mx_to_torch_sparse_tensor (:51-57).  Output equals
+ * that tensor's .coalesce().to_sparse_csr() bit for bit.
+ * capacity = 2*n_triples + n_ent entries for col/val outputs.
+ * SYNCHRONOUS: waits for the stream so *h_nnz is valid on return.
+ */
+size_t eg_adj_workspace_bytes(int64_t n_triples, int64_t n_ent);
+int eg_adj_build(const int64_t* heads, const int64_t* tails, int64_t n_triples, int64_t n_ent,
+                 void* ws, size_t ws_bytes,
+                 int64_t* crow /* [n_ent+1] */, int64_t* col /* [capacity] */, float* val /* [capacity] */,
+                 int32_t* rowptr32 /* [n_ent+1] */, int32_t* col32 /* [capacity] */,
+                 int64_t* h_nnz /* host */, eg_stream_t stream);
+
+/* CSR -> CSR of the transpose (for dH = A^T dS; layers/layers.py:35,64 autograd).
+ * Entries of each output row are ordered by ascending source row. */
+size_t eg_csr_transpose_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);
+int eg_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                     const int32_t* rowptr, const int32_t* col, const float* val,
+                     void* ws, size_t ws_bytes,
+                     int32_t* rowptr_t /* [n_cols+1] */, int32_t* col_t /* [nnz] */, float* val_t /* [nnz] */,
+                     eg_stream_t stream);
+
+/* ---- (a) message-passing SpMM with fused epilogue ----------------------------
+ * Replaces torch.spmm(adj, hidden) + act + highway blend, layers/layers.py:35-38
+ * and :64-76:   S = A·H;  a = act(S);
+ *   gate_pre == NULL : out = a
+ *   gate_pre != NULL : t = sigmoid(gate_pre); out = t*a + (1-t)*x_res
+ * act_out (nullable) receives a = act(S) for the backward pass.
+ * Rows longer than `long_row_threshold` are split into segments listed in
+ * seg_* (built by the host mirror once per adjacency; n_seg may be 0); their
+ * partial sums go through `seg_scratch` [n_seg, d] and are finished by a second
+ * small launch over long_rows[n_long] / long_first[n_long+1].
+ * H, out, gate_pre, x_res, act_out: [n_rows or n_cols, d] fp32, 16-byte aligned
+ * when d % 4 == 0.
+ */
+int eg_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
+            const float* H, int d, int act,
+            const float* gate_pre, const float* x_res,
+            float* out, float* act_out,
+            int long_row_threshold,
+            const int32_t* seg_row, const int32_t* seg_begin, const int32_t* seg_end, int64_t n_seg,
+            const int32_t* long_rows, const int32_t* long_first, int64_t n_long,
+            float* seg_scratch, eg_stream_t stream);
+
+/* Element-wise backward of the fused epilogue (autograd of layers/layers.py:67-76):
+ *   dS      = dout * t * act'(S)           (t = 1 when gate_pre == NULL)
+ *   d_gate  = dout * (a - x_res) * t*(1-t) (nullable)
+ *   d_xres  = dout * (1 - t)               (nullable)
+ * `a` is act_out saved by eg_spmm (relu mask = a > 0). */
+int eg_epilogue_bwd(const float* dout, const float* a, const float* gate_pre, const float* x_res,
+                    int64_t n_elem, int act, float* dS, float* d_gate, float* d_xres, eg_stream_t stream);
+
+/* ---- (c) alignment evaluation: exact fp64 L1 distances + ranks/top-k/argmin ---
+ * Replaces scipy.spatial.distance.cdist(..., 'cityblock') at
+ * utils/eval_utils.py:74 and models/models_ea.py:24,149: fp32 inputs widened to
+ * fp64, |l-r| summed over k = 0..d-1 in that order, so the result is bit-equal
+ * to SciPy's.  D is [nL, ldD] fp64 (ldD >= nR). */
+int eg_l1_matrix(const float* L, int64_t nL, const float* R, int64_t nR, int d,
+                 double* D, int64_t ldD, eg_stream_t stream);
+/* diag[i] = sum_k |L[i,k] - R[i,k]|, same summation order as eg_l1_matrix. */
+int eg_l1_paired(const float* L, const float* R, int64_t n, int d, double* diag, eg_stream_t stream);
+/* Rank of the true match (utils/eval_utils.py:77-89, stable tie order): for the
+ * row block [row0, row0+n_rows) of a score matrix D (fp64, [n_rows, ldD], n_cols
+ * columns): rank_row[row0+i] = #{j : D[i,j] < diag[row0+i]} + #{j < row0+i : ==},
+ * and rank_col[j] += #{i : D[i,j] < diag[j]} + #{row0+i < j : ==}.
+ * rank_col must be zeroed by the caller before the first block. */
+int eg_rank_accumulate(const double* D, int64_t ldD, int64_t row0, int64_t n_rows, int64_t n_cols,
+                       const double* diag, int32_t* rank_row, int32_t* rank_col, eg_stream_t stream);
+/* Row / column arg-min with lowest-index ties (utils/eval_utils.py:167,
+ * models/models_ea.py:151-153).  Column results are merged into col_min/col_arg
+ * across successive row blocks (caller initialises col_min=+inf, col_arg=-1). */
+int eg_argmin_accumulate(const double* D, int64_t ldD, int64_t row0, int64_t n_rows, int64_t n_cols,
+                         double* row_min, int64_t* row_arg, double* col_min, int64_t* col_arg,
+                         eg_stream_t stream);
+/* Per row the indices ranked [skip, skip+k) by (value, index) ascending
+ * (models/models_ea.py:26-27: argsort()[1:k+1]).  skip+k <= 2048. */
+int eg_topk_rows(const double* D, int64_t ldD, int64_t n_rows, int64_t n_cols,
+                 int skip, int k, int64_t* out_idx /* [n_rows, k] */, eg_stream_t stream);
+
+/* ---- (b) Sinkhorn, log domain --------------------------------------------------
+ * One half-sweep ("pass") on a MATERIALISED cost (utils/ot_loss.py:53-55 and
+ * SinkhornOT/sinkhorn_loss.py:197-201 in log form):
+ *     lse[i]     = log sum_j exp(pot_in[j] - M[i,j] * inv_reg)
+ *     pot_out[i] = logw[i] - lse[i]
+ * for every row i of M [n_rows, ld].  The column half-sweep is the same call on
+ * the transposed cost (eg_transpose).  dtype: 0 = fp32, 1 = fp64 for M, pot_*,
+ * logw, lse alike.  lse_out nullable. */
+int eg_lse_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, int64_t ld, double inv_reg,
+                 const void* pot_in, const void* logw, void* pot_out, void* lse_out, eg_stream_t stream);
+int eg_transpose(int dtype, const void* src, int64_t n_rows, int64_t n_cols, int64_t ld_src,
+                 void* dst, int64_t ld_dst, eg_stream_t stream);
+/* Plan and primal cost (utils/ot_loss.py:75-76): P[i,j] = exp(f[i] + g[j] - M[i,j]*inv_reg)
+ * (P nullable), *loss = sum P∘M (fp64), row_sum / col_sum (nullable, dtype-typed)
+ * receive the marginals.  loss/row_sum/col_sum are zeroed by the call itself. */
+int eg_plan_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, int64_t ld, double inv_reg,
+                  const void* f, const void* g, void* P, int64_t ldP, double* loss,
+                  void* row_sum, void* col_sum, eg_stream_t stream);
+/* Whole solver of utils/ot_loss.py:26-76 on the device (materialised cost):
+ * u0 = 1/I, v0 = 1/J, column then row update per sweep, marginal-error check on
+ * sweeps 0,10,20,…, stop at err <= stop_thr or max_iter.  Mt is scratch for the
+ * transposed cost [n_cols, n_rows].  log_u/log_v receive the final log-scalings.
+ * SYNCHRONOUS every 10 sweeps (error read-back), h_* are host outputs. */
+int eg_sinkhorn_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, double reg,
+                      const void* a, const void* b, int max_iter, double stop_thr,
+                      void* Mt, void* log_u, void* log_v, void* ws, size_t ws_bytes,
+                      int* h_sweeps, double* h_err, eg_stream_t stream);
+size_t eg_sinkhorn_dense_workspace_bytes(int dtype, int64_t n_rows, int64_t n_cols);
+
+/* FUSED half-sweep: the cost tile is recomputed from the two embedding sets and
+ * reduced straight into the row log-sum-exp; M is never written
+ * (models/models_ea.py:218 + utils/ot_loss.py:53-55 fused).
+ *     lse[i] = log sum_j exp(pot_in[j] - cost(A_i, B_j) * inv_reg),  pot_out = logw - lse
+ * A [nA, d], B [nB, d] fp32.  Call with (A,B) = (X,Y) for the row update and
+ * (Y,X) for the column update.  normA/normB: squared row norms (L2, SQEUCLID) or
+ * row norms (COSINE), from eg_row_norms.  algo: EG_ALGO_SIMT (fp32 FMA tiles) or
+ * EG_ALGO_TCGEN05 (TMA-fed tcgen05 3xTF32 tiles; needs the split operands from
+ * eg_split_tf32 passed as A_hi/A_lo/B_hi/B_lo, else NULL). */
+int eg_row_norms(const float* A, int64_t n, int d, int squared, float* out, eg_stream_t stream);
+int eg_lse_fused(int algo, int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,
+                 const float* normA, const float* normB, float inv_reg,
+                 const float* pot_in, const float* logw, float* pot_out, float* lse_out,
+                 const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
+                 void* ws, size_t ws_bytes, eg_stream_t stream);
+size_t eg_lse_fused_workspace_bytes(int algo, int64_t nA, int64_t nB, int d);
+/* hi = tf32(x) (round-to-nearest, low 13 mantissa bits zero), lo = tf32(x - hi);
+ * rows are zero-padded from d to d_pad columns (d_pad % 8 == 0). */
+int eg_split_tf32(const float* X, int64_t n, int d, int d_pad, float* hi, float* lo, eg_stream_t stream);
+/* Fused plan statistics: *loss = sum_ij P_ij * cost_ij with P = exp(f_i + g_j - cost*inv_reg);
+ * row_sum[i] (nullable) = sum_j P_ij (both zeroed by the call).  P (nullable) [nA, ldP]
+ * is written only on request. */
+int eg_plan_fused(int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,
+                  const float* normA, const float* normB, float inv_reg,
+                  const float* f, const float* g, float* P, int64_t ldP, double* loss, float* row_sum,
+                  eg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAGRAFT_H_ */
