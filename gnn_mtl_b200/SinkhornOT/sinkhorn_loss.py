@@ -7,10 +7,13 @@ log form the absorbed and un-absorbed states are the same numbers, so here the
 sweeps run on alpha = u/eps + log a and beta = v/eps + log b directly; the
 absorption schedule only decides WHEN the primal cost is evaluated and the
 stopping test made (sweeps 0, 10, 20, … and the last), which is reproduced.
-The 1e30 / 1e20 clamps of the reference (:14-15,184-188,203) guard overflow that
-cannot happen in log form and are not emulated.
+The reference's clamp a, b <= 1e30 (:14-15,197-201) and its early absorption when
+a or b exceeds 1e20 (:203) are reproduced in log form (they change the iterates
+for small eps); the clamp on K itself (:184-188) cannot trigger once a, b are bounded.
 """
 from __future__ import annotations
+
+import math
 
 import torch
 
@@ -25,20 +28,35 @@ def kl_div(x, y):
     return torch.mul(y, div * torch.log(div + small) - div + 1)
 
 
+LOG_HUGE = math.log(1e30)   # myclamp upper bound of the reference (:12,14-15)
+LOG_BIG = math.log(1e20)    # early-absorption trigger (:11,203)
+
+
 def _solve_one(C, mu, nu, epsilon, numIterMax, tol):
+    """alpha = u/eps + log a, beta = v/eps + log b of the reference's state; (u_abs, v_abs)
+    are the potentials as of the last absorption, needed only to reproduce the
+    reference's clamp a, b <= 1e30 (it bites for small eps in the first sweeps) and
+    its "absorb when a or b exceeds 1e20" rule, which adds stopping tests."""
     I, J = C.shape
     inv = 1.0 / epsilon
     Ct = ops.transpose(C)
     log_mu, log_nu = torch.log(mu), torch.log(nu)
     alpha = torch.zeros(I, dtype=C.dtype, device=C.device)
     beta = torch.zeros(J, dtype=C.dtype, device=C.device)
+    u_abs, v_abs = alpha, beta
     _, transport, _, _ = ops.plan_dense(C, inv, alpha, beta, want_plan=False)
     transport = transport.to(C.dtype)
     transport_new = transport
     for ii in range(numIterMax):
         alpha, _ = ops.lse_dense(C, inv, beta, log_mu)      # a = mu / (K b)
+        alpha = torch.minimum(alpha, u_abs + LOG_HUGE)
         beta, _ = ops.lse_dense(Ct, inv, alpha, log_nu)     # b = nu / (K^T a)
-        if ii % 10 == 0 or ii == numIterMax - 1:
+        beta = torch.minimum(beta, v_abs + LOG_HUGE)
+        absorb = ii % 10 == 0 or ii == numIterMax - 1
+        if not absorb:
+            absorb = bool(((alpha - u_abs).max() > LOG_BIG) | ((beta - v_abs).max() > LOG_BIG))
+        if absorb:
+            u_abs, v_abs = alpha, beta
             _, transport_new, _, _ = ops.plan_dense(C, inv, alpha, beta, want_plan=False)
             transport_new = transport_new.to(C.dtype)
             if abs(transport_new - transport) / abs(transport) < tol:

@@ -85,21 +85,43 @@ lse_rows_kernel(const T* __restrict__ M, int64_t n_rows, int64_t n_cols, int64_t
     if constexpr (sizeof(T) == 4) {
       const float4* m4 = reinterpret_cast<const float4*>(mrow);
       const float4* p4 = reinterpret_cast<const float4*>(pot_in);
-      for (int64_t v = sub * 32 + lane; v < n_vec; v += stride) {
-        float4 mv = ld_stream_f4(m4 + v);
-        float4 pv = __ldg(p4 + v);
-        acc.push4(fmaf(-mv.x, inv_reg, pv.x), fmaf(-mv.y, inv_reg, pv.y), fmaf(-mv.z, inv_reg, pv.z),
-                  fmaf(-mv.w, inv_reg, pv.w));
+      constexpr int U = 4;   // 16-byte loads in flight per lane before any math
+      for (int64_t v0 = sub * 32 + lane; v0 < n_vec; v0 += (int64_t)stride * U) {
+        float4 mv[U], pv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          int64_t v = v0 + (int64_t)u * stride;
+          if (v < n_vec) {
+            mv[u] = ld_stream_f4(m4 + v);
+            pv[u] = __ldg(p4 + v);
+          } else {
+            mv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pv[u] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          acc.push4(fmaf(-mv[u].x, inv_reg, pv[u].x), fmaf(-mv[u].y, inv_reg, pv[u].y),
+                    fmaf(-mv[u].z, inv_reg, pv[u].z), fmaf(-mv[u].w, inv_reg, pv[u].w));
       }
     } else {
       const double2* m2 = reinterpret_cast<const double2*>(mrow);
       const double2* p2 = reinterpret_cast<const double2*>(pot_in);
-      for (int64_t v = sub * 32 + lane; v < n_vec; v += stride) {
-        double2 mv = m2[v];
-        double2 pv = p2[v];
-        // pot - M/reg evaluated as the reference does (division by reg folded into inv_reg)
-        acc.push1(pv.x - mv.x * inv_reg);
-        acc.push1(pv.y - mv.y * inv_reg);
+      constexpr int U = 4;
+      for (int64_t v0 = sub * 32 + lane; v0 < n_vec; v0 += (int64_t)stride * U) {
+        double2 mv[U], pv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          int64_t v = v0 + (int64_t)u * stride;
+          if (v < n_vec) { mv[u] = m2[v]; pv[u] = p2[v]; }
+          else { mv[u] = make_double2(0.0, 0.0); pv[u] = make_double2(-CUDART_INF, -CUDART_INF); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          // pot - M/reg (division by reg folded into inv_reg)
+          acc.push1(pv[u].x - mv[u].x * inv_reg);
+          acc.push1(pv[u].y - mv[u].y * inv_reg);
+        }
       }
     }
     for (int64_t j = n_vec * V + sub * 32 + lane; j < n_cols; j += stride)
@@ -213,18 +235,23 @@ __global__ void marginal_err_kernel(const T* __restrict__ log_v, const T* __rest
 template <typename T>
 static int lse_dense_t(const T* M, int64_t n_rows, int64_t n_cols, int64_t ld, double inv_reg, const T* pot_in,
                        const T* logw, T* pot_out, T* lse_out, cudaStream_t s) {
-  // few long rows -> more warps per row so the machine stays full
-  int64_t warps_needed = n_rows;
-  if (warps_needed >= 148 * 32 || n_cols <= 1024) {
+  // pick warps-per-row so that >= ~3 warps/SM-slot-quarter are resident and each lane still
+  // sees a few 16-byte vectors: rows*wpr >= 148*64 when the row is long enough
+  const int64_t vec_per_row = n_cols / (16 / (int64_t)sizeof(T));
+  int wpr = 1;
+  while (wpr < 8 && n_rows * wpr < (int64_t)kNumSMs * 64 && vec_per_row / (32 * wpr * 2) >= 2) wpr *= 2;
+  if (wpr == 1)
     lse_rows_kernel<T, 1><<<(unsigned)ceil_div(n_rows, 8), 256, 0, s>>>(M, n_rows, n_cols, ld, (T)inv_reg, pot_in,
                                                                          logw, pot_out, lse_out);
-  } else if (warps_needed * 2 >= 148 * 16 || n_cols <= 4096) {
+  else if (wpr == 2)
     lse_rows_kernel<T, 2><<<(unsigned)ceil_div(n_rows, 4), 256, 0, s>>>(M, n_rows, n_cols, ld, (T)inv_reg, pot_in,
                                                                          logw, pot_out, lse_out);
-  } else {
+  else if (wpr == 4)
+    lse_rows_kernel<T, 4><<<(unsigned)ceil_div(n_rows, 2), 256, 0, s>>>(M, n_rows, n_cols, ld, (T)inv_reg, pot_in,
+                                                                         logw, pot_out, lse_out);
+  else
     lse_rows_kernel<T, 8><<<(unsigned)n_rows, 256, 0, s>>>(M, n_rows, n_cols, ld, (T)inv_reg, pot_in, logw,
                                                            pot_out, lse_out);
-  }
   EG_LAUNCHED();
   return EG_OK;
 }

@@ -13,8 +13,12 @@
 
 namespace eg {
 
-constexpr int kWarpsPerBlock = 8;
-constexpr int kUnroll = 4;  // neighbour rows in flight per warp (x VPL float4 each)
+constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
+
+// Tuning knobs (defaults chosen from the ncu study in profiles/); eg_debug_set() overrides them.
+int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each)
+int g_tune_warps = 4;       // warps (= rows) per CTA
+int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
 
 struct Epilogue {
   const float* gate_pre;
@@ -24,16 +28,57 @@ struct Epilogue {
   int act;
 };
 
+struct Policies {
+  unsigned long long keep, stream;
+  bool on;
+};
+
+__device__ __forceinline__ Policies make_policies(bool on) {
+  Policies p;
+  p.on = on;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  return p;
+}
+
+// feature-row gather: keep in L2 (rows are re-read by other warps)
+__device__ __forceinline__ float4 ld_keep_f4(const float4* ptr, const Policies& p) {
+  float4 r;
+  if (p.on)
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(p.keep));
+  else
+    r = __ldg(ptr);
+  return r;
+}
+// touched-once data: do not displace the feature rows
+__device__ __forceinline__ float4 ld_once_f4(const float4* ptr, const Policies& p) {
+  float4 r;
+  if (p.on)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(p.stream));
+  else
+    r = ld_stream_f4(ptr);
+  return r;
+}
+__device__ __forceinline__ void st_once_f4(float4* ptr, const float4& v, const Policies& p) {
+  if (p.on)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(p.stream) : "memory");
+  else
+    st_stream_f4(ptr, v);
+}
+
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + expf(-z)); }
 
-__device__ __forceinline__ float4 apply_epilogue(const Epilogue& ep, float4 s, int64_t off4) {
+__device__ __forceinline__ float4 apply_epilogue(const Epilogue& ep, float4 s, int64_t off4, const Policies& pol) {
   if (ep.act == EG_ACT_RELU) {
     s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
   }
-  if (ep.act_out) st_stream_f4(reinterpret_cast<float4*>(ep.act_out) + off4, s);
+  if (ep.act_out) st_once_f4(reinterpret_cast<float4*>(ep.act_out) + off4, s, pol);
   if (ep.gate_pre) {
-    float4 g = ld_stream_f4(reinterpret_cast<const float4*>(ep.gate_pre) + off4);
-    float4 x = ld_stream_f4(reinterpret_cast<const float4*>(ep.x_res) + off4);
+    float4 g = ld_once_f4(reinterpret_cast<const float4*>(ep.gate_pre) + off4, pol);
+    float4 x = ld_once_f4(reinterpret_cast<const float4*>(ep.x_res) + off4, pol);
     float t;
     t = sigmoidf_(g.x); s.x = t * s.x + (1.0f - t) * x.x;
     t = sigmoidf_(g.y); s.y = t * s.y + (1.0f - t) * x.y;
@@ -53,12 +98,12 @@ __device__ __forceinline__ float apply_epilogue1(const Epilogue& ep, float s, in
   return s;
 }
 
-// acc += sum_{i in [b,e)} val[i] * H[col[i], chunk], VPL float4 per lane, kUnroll rows in flight.
+// acc += sum_{i in [b,e)} val[i] * H[col[i], chunk], VPL float4 per lane, UNROLL rows in flight.
 // `Hc` already points at the column chunk; `d4` is the full row stride in float4.
-template <int VPL>
+template <int VPL, int UNROLL>
 __device__ __forceinline__ void gather_rows(const int32_t* __restrict__ col, const float* __restrict__ val,
                                             const float4* __restrict__ Hc, int d4, int d4_local, int b, int e,
-                                            int lane, float4 (&acc)[VPL]) {
+                                            int lane, const Policies& pol, float4 (&acc)[VPL]) {
   for (int base = b; base < e; base += 32) {
     int idx = base + lane;
     int my_col = 0;
@@ -68,11 +113,11 @@ __device__ __forceinline__ void gather_rows(const int32_t* __restrict__ col, con
       my_val = ld_stream_f32(val + idx);
     }
     int cnt = min(32, e - base);
-    for (int t = 0; t < cnt; t += kUnroll) {
-      float4 x[kUnroll][VPL];
-      float v[kUnroll];
+    for (int t = 0; t < cnt; t += UNROLL) {
+      float4 x[UNROLL][VPL];
+      float v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         int c = __shfl_sync(0xffffffffu, my_col, (t + u) & 31);
         float vv = __shfl_sync(0xffffffffu, my_val, (t + u) & 31);
         bool live = (t + u < cnt);
@@ -81,11 +126,11 @@ __device__ __forceinline__ void gather_rows(const int32_t* __restrict__ col, con
 #pragma unroll
         for (int p = 0; p < VPL; ++p) {
           int k = lane + 32 * p;
-          x[u][p] = (live && k < d4_local) ? __ldg(rowp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[u][p] = (live && k < d4_local) ? ld_keep_f4(rowp + k, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
         for (int p = 0; p < VPL; ++p) {
           acc[p].x = fmaf(v[u], x[u][p].x, acc[p].x);
@@ -100,15 +145,17 @@ __device__ __forceinline__ void gather_rows(const int32_t* __restrict__ col, con
 
 // Warps [0, n_rows): one short row each (rows longer than `thresh` are skipped here).
 // Warps [n_rows, n_rows + n_seg): one segment of a long row each -> seg_scratch.
-template <int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int VPL, int UNROLL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 spmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const float* __restrict__ val, int64_t n_rows, const float* __restrict__ H, int d4,
                 int chunk0, Epilogue ep, int thresh, const int32_t* __restrict__ seg_begin,
-                const int32_t* __restrict__ seg_end, int64_t n_seg, float* __restrict__ seg_scratch) {
+                const int32_t* __restrict__ seg_end, int64_t n_seg, float* __restrict__ seg_scratch,
+                int hints) {
   int lane = threadIdx.x & 31;
-  int64_t w = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  int64_t w = blockIdx.x * (int64_t)WARPS + (threadIdx.x >> 5);
   if (w >= n_rows + n_seg) return;
+  const Policies pol = make_policies(hints != 0);
   const float4* Hc = reinterpret_cast<const float4*>(H) + chunk0;
   int d4_local = min(d4 - chunk0, 32 * VPL);
   float4 acc[VPL];
@@ -117,19 +164,19 @@ spmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   if (w < n_rows) {
     int b = rowptr[w], e = rowptr[w + 1];
     if (e - b > thresh) return;
-    gather_rows<VPL>(col, val, Hc, d4, d4_local, b, e, lane, acc);
+    gather_rows<VPL, UNROLL>(col, val, Hc, d4, d4_local, b, e, lane, pol, acc);
 #pragma unroll
     for (int p = 0; p < VPL; ++p) {
       int k = lane + 32 * p;
       if (k < d4_local) {
         int64_t off4 = w * d4 + chunk0 + k;
-        float4 r = apply_epilogue(ep, acc[p], off4);
-        st_stream_f4(reinterpret_cast<float4*>(ep.out) + off4, r);
+        float4 r = apply_epilogue(ep, acc[p], off4, pol);
+        st_once_f4(reinterpret_cast<float4*>(ep.out) + off4, r, pol);
       }
     }
   } else {
     int64_t sidx = w - n_rows;
-    gather_rows<VPL>(col, val, Hc, d4, d4_local, seg_begin[sidx], seg_end[sidx], lane, acc);
+    gather_rows<VPL, UNROLL>(col, val, Hc, d4, d4_local, seg_begin[sidx], seg_end[sidx], lane, pol, acc);
     float4* dst = reinterpret_cast<float4*>(seg_scratch) + sidx * d4 + chunk0;
 #pragma unroll
     for (int p = 0; p < VPL; ++p) {
@@ -213,23 +260,47 @@ __global__ void epilogue_bwd_kernel(const float* __restrict__ dout, const float*
   }
 }
 
+template <int VPL, int UNROLL, int WARPS>
+static int launch_vec3(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
+                       const float* H, int d4, int chunk0, const Epilogue& ep, int thresh,
+                       const int32_t* seg_begin, const int32_t* seg_end, int64_t n_seg, float* seg_scratch,
+                       cudaStream_t s) {
+  int64_t warps = n_rows + n_seg;
+  unsigned grid = (unsigned)ceil_div(warps, WARPS);
+  spmm_vec_kernel<VPL, UNROLL, WARPS><<<grid, WARPS * 32, 0, s>>>(rowptr, col, val, n_rows, H, d4, chunk0, ep,
+                                                                   thresh, seg_begin, seg_end, n_seg,
+                                                                   seg_scratch, g_tune_hints);
+  EG_LAUNCHED();
+  return EG_OK;
+}
+
 template <int VPL>
 static int launch_vec(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
                       const float* H, int d4, int chunk0, const Epilogue& ep, int thresh,
                       const int32_t* seg_begin, const int32_t* seg_end,
                       int64_t n_seg, float* seg_scratch, cudaStream_t s) {
-  int64_t warps = n_rows + n_seg;
-  unsigned grid = (unsigned)ceil_div(warps, kWarpsPerBlock);
-  spmm_vec_kernel<VPL><<<grid, kWarpsPerBlock * 32, 0, s>>>(rowptr, col, val, n_rows, H, d4, chunk0, ep,
-                                                             thresh, seg_begin, seg_end, n_seg,
-                                                             seg_scratch);
-  EG_LAUNCHED();
-  return EG_OK;
+#define EG_SPMM_CASE(U, W)                                                                              \
+  if (g_tune_unroll == U && g_tune_warps == W)                                                          \
+    return launch_vec3<VPL, U, W>(rowptr, col, val, n_rows, H, d4, chunk0, ep, thresh, seg_begin, seg_end, \
+                                  n_seg, seg_scratch, s);
+  EG_SPMM_CASE(4, 8) EG_SPMM_CASE(2, 8) EG_SPMM_CASE(4, 4) EG_SPMM_CASE(2, 4) EG_SPMM_CASE(1, 8) EG_SPMM_CASE(8, 4)
+#undef EG_SPMM_CASE
+  return launch_vec3<VPL, 2, 4>(rowptr, col, val, n_rows, H, d4, chunk0, ep, thresh, seg_begin, seg_end, n_seg,
+                                seg_scratch, s);
 }
 
 }  // namespace eg
 
 extern "C" {
+
+// Undeclared tuning hook used by tools/ only (not part of include/eagraft.h).
+int eg_debug_set(int key, int value) {
+  if (key == 0) eg::g_tune_unroll = value;
+  else if (key == 1) eg::g_tune_warps = value;
+  else if (key == 2) eg::g_tune_hints = value;
+  else return EG_ERR_INVALID;
+  return EG_OK;
+}
 
 int eg_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, const float* H,
             int d, int act, const float* gate_pre, const float* x_res, float* out, float* act_out,

@@ -127,19 +127,30 @@ class UEAModel(BaseModel):
         return _margin_loss(outputs, self.ILL, self.neg_left, self.neg_right, self.neg2_left,
                             self.neg2_right, self.neg_num)
 
-    def get_loss_wassertein(self, outputs, data, bsz, *, numItermax=1000, stopThr=1e-9):
+    def get_loss_wassertein(self, outputs, data, bsz, *, numItermax=1000, stopThr=1e-9, sample=None):
         """:206-224, quirk included: the Sinkhorn plan is computed and then not
         used — the one-hot is taken from argmax of a zero tensor, i.e. column 0 —
-        so the value (and its gradient) is sum_i ||X_i - Y_0||_2."""
-        e1, e2 = data['e1'], data['e2']
-        index1, index2 = data['index1'], data['index2']
-        L = np.array([index1[i] for i in np.random.permutation(e1)[:bsz]])
-        R = np.array([index2[i] for i in np.random.permutation(e2)[:bsz]])
+        so the value (and its gradient) is sum_i ||X_i - Y_0||_2.
+
+        ``sample`` (keyword-only extension): a pair of int64 CUDA index tensors to
+        use instead of drawing np.random.permutation on the host (:211-212)."""
         dev = outputs.device
-        X = outputs[torch.as_tensor(L, device=dev)]
-        Y = outputs[torch.as_tensor(R, device=dev)]
+        if sample is None:
+            e1, e2 = data['e1'], data['e2']
+            index1, index2 = data['index1'], data['index2']
+            L = np.array([index1[i] for i in np.random.permutation(e1)[:bsz]])
+            R = np.array([index2[i] for i in np.random.permutation(e2)[:bsz]])
+            sample = (_host_to_device(L, dev), _host_to_device(R, dev))
+        X = outputs[sample[0]]
+        Y = outputs[sample[1]]
         a, b = torch.ones(bsz, device=dev), torch.ones(bsz, device=dev)
         M = torch.cdist(X, Y, p=2)
         T, _ = sinkhorn(a, b, M.detach(), reg=0.01, numItermax=numItermax, stopThr=stopThr, return_plan=False)
         # newT = one-hot(argmax(zeros)) = column 0 of every row (reference :221-222)
         return torch.sum(M[:, 0].to(torch.float64))
+
+
+def _host_to_device(arr, dev):
+    """Host index array -> CUDA tensor through pinned memory (async H2D)."""
+    staged = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).pin_memory()
+    return staged.to(dev, non_blocking=True)

@@ -18,6 +18,9 @@ def _f32c(t):
 
 # ---- (a) SpMM ----------------------------------------------------------------
 
+# bench.py sets this to a list to collect (start_event, end_event, csr, d, fused, saved) per launch
+SPMM_TIMER = None
+
 def spmm(csr, H, act=_lib.ACT_IDENTITY, gate_pre=None, x_res=None, save_act=False):
     """out = epilogue(csr · H); returns (out, act_out or None)."""
     _lib.require_cuda(H, gate_pre, x_res)
@@ -30,11 +33,18 @@ def spmm(csr, H, act=_lib.ACT_IDENTITY, gate_pre=None, x_res=None, save_act=Fals
     out = torch.empty(n_rows, d, dtype=torch.float32, device=H.device)
     act_out = torch.empty_like(out) if save_act else None
     with torch.cuda.device(H.device):
+        scratch = csr.scratch(d)
+        if SPMM_TIMER is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(lib.eg_spmm(ptr(csr.rowptr), ptr(csr.col), ptr(csr.val), n_rows, ptr(H), d, act,
                           ptr(gate_pre), ptr(x_res), ptr(out), ptr(act_out), csr.threshold,
                           ptr(csr.seg_row), ptr(csr.seg_begin), ptr(csr.seg_end), csr.n_seg,
-                          ptr(csr.long_rows), ptr(csr.long_first), csr.n_long, ptr(csr.scratch(d)), stream()),
+                          ptr(csr.long_rows), ptr(csr.long_first), csr.n_long, ptr(scratch), stream()),
               "eg_spmm")
+        if SPMM_TIMER is not None:
+            ev1.record()
+            SPMM_TIMER.append((ev0, ev1, csr, d, gate_pre is not None, save_act))
     return out, act_out
 
 
