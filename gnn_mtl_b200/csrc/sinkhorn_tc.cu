@@ -1,16 +1,404 @@
-// (b) TMA + tcgen05 (3xTF32) cost-tile path of the fused Sinkhorn half-sweep.
-// Placeholder until the tensor-core kernel lands: reports "unsupported" so callers
-// fail loudly instead of silently taking another path.
+// (b) Fused Sinkhorn half-sweep on the 5th-gen tensor cores (sm_100a only).
+//
+//   lse[i] = log sum_j exp(pot[j] - cost(A_i, B_j) * inv_reg)
+//
+// The 128 x 256 tile of dot products A_i·B_j is produced by tcgen05.mma (kind::tf32)
+// with both operands fed by TMA (cp.async.bulk.tensor, 128-byte swizzle) and the
+// accumulator living in TMEM; fp32 accuracy comes from the 3xTF32 split
+//   a·b ≈ a_hi·b_hi + a_hi·b_lo + a_lo·b_hi      (hi = tf32(x), lo = tf32(x - hi), eg_split_tf32)
+// issued as three MMAs per k-step into the same accumulator.  The epilogue reads
+// the accumulator back with tcgen05.ld (one TMEM lane = one row of A = one
+// thread), turns dots into costs, and folds them into a per-thread online
+// log-sum-exp — the I x J cost is never written anywhere.  Two accumulator
+// buffers (2 x 256 TMEM columns) let the epilogue of tile t overlap the MMAs of
+// tile t+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer, warps 2-5 = epilogue (TMEM lane quadrant = warp_id % 4).
+#include <cuda.h>
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace eg {
 
-size_t lse_fused_tc_workspace(int64_t, int64_t, int) { return 256; }
+namespace tc {
 
-int lse_fused_tc(int, int64_t, int64_t, int, const float*, const float*, float, const float*, const float*,
-                 float*, float*, const float*, const float*, const float*, const float*, void*, size_t,
-                 cudaStream_t) {
-  return EG_ERR_UNSUPPORTED;
+constexpr int BM = 128;          // rows of A per tile  (UMMA M)
+constexpr int BN = 256;          // rows of B per tile  (UMMA N)
+constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle atom
+constexpr int UK = 8;            // K per tcgen05.mma for tf32
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 4;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 8 + 256 + 1024;  // + (norm,pot) staging + barriers + align
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
+                                            int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address  [0,14)
+  desc |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major)
+  desc |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  desc |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  desc |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return desc;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Params {
+  int64_t nA, nB;
+  int k_blocks;            // ceil(d_pad / BK)
+  int d_pad;               // operand row length (multiple of 8)
+  int cost;
+  float inv_reg;
+  const float* normA;
+  const float* normB;
+  const float* pot_in;
+  int tiles_per_split;     // B tiles handled by one CTA (grid.y = splits)
+  float* part_m;           // [splits, nA]
+  float* part_s;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;                                     // STAGES * 96 KB, 1024-aligned tiles
+  float2* colinfo = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES);   // [2][BN] (norm_b, pot_b)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2 * BN * 8);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * BM;
+  const int n_btiles = (int)((p.nB + BN - 1) / BN);
+  const int t_begin = blockIdx.y * p.tiles_per_split;
+  const int t_end = min(n_btiles, t_begin + p.tiles_per_split);
+  const int n_tiles = max(t_end - t_begin, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation is a warp-wide instruction; this warp also frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = (t_begin + t) * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = stage_base + s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_2d(st, &map_a_hi, &full[s], kb * BK, (int)i0);
+          tma_load_2d(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, (int)i0);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full[s], kb * BK, j0);
+          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[s], kb * BK, j0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t use = (uint32_t)(t >> 1);           // how many times this buffer was used before
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);            // epilogue has drained the buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(stage_base + s * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(st);
+          const uint64_t a_lo = make_smem_desc(st + A_TILE_BYTES);
+          const uint64_t b_hi = make_smem_desc(st + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          // the last k-block may be partly past d_pad (TMA zero-fills it): skip those k-steps
+          const int k_steps = min(BK / UK, (p.d_pad - kb * BK) / UK);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            if (k >= k_steps) break;
+            const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);   // 32 B per k-step, in 16-byte units
+            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+            umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+            umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
+          }
+          umma_commit(&empty[s]);                           // smem stage reusable once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[buf]);                           // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, one TMEM lane (= row of A) per thread =====================
+    const int ep_tid = threadIdx.x - 64;                     // 0..127
+    const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
+    const int row_in_tile = quad * 32 + lane;
+    const int64_t row = i0 + row_in_tile;
+    const float na = (row < p.nA) ? p.normA[row] : 0.f;
+    float run_m = -CUDART_INF_F, run_s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = (int64_t)(t_begin + t) * BN;
+      // stage (norm_b, pot_b) for this tile; buffer `buf` was last read two tiles ago
+      float2* ci = colinfo + buf * BN;
+      for (int c = ep_tid; c < BN; c += 128) {
+        int64_t j = j0 + c;
+        ci[c] = (j < p.nB) ? make_float2(p.normB[j], p.pot_in[j]) : make_float2(0.f, -CUDART_INF_F);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float dot[32];
+        tmem_ld32(taddr + (uint32_t)c0, dot);
+        float z[32];
+        float zmax = -CUDART_INF_F;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float4 info = *reinterpret_cast<const float4*>(&ci[c0 + c]);   // (nb0, pot0, nb1, pot1)
+          float cst0, cst1;
+          if (p.cost == EG_COST_COSINE) {
+            cst0 = 1.0f - __fdividef(dot[c], fmaxf(na, 1e-8f) * fmaxf(info.x, 1e-8f));
+            cst1 = 1.0f - __fdividef(dot[c + 1], fmaxf(na, 1e-8f) * fmaxf(info.z, 1e-8f));
+          } else {
+            float sq0 = fmaxf(fmaf(-2.0f, dot[c], na + info.x), 0.f);
+            float sq1 = fmaxf(fmaf(-2.0f, dot[c + 1], na + info.z), 0.f);
+            cst0 = (p.cost == EG_COST_L2) ? fast_sqrt(sq0) : sq0;
+            cst1 = (p.cost == EG_COST_L2) ? fast_sqrt(sq1) : sq1;
+          }
+          z[c] = fmaf(-cst0, p.inv_reg, info.y);       // pot = -inf on padded columns -> z = -inf
+          z[c + 1] = fmaf(-cst1, p.inv_reg, info.w);
+          zmax = fmaxf(zmax, fmaxf(z[c], z[c + 1]));
+        }
+        if (zmax > run_m) { run_s *= __expf(run_m - zmax); run_m = zmax; }
+        if (run_m > -CUDART_INF_F) {
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc += __expf(z[c] - run_m);
+          run_s += acc;
+        }
+      }
+      // release the accumulator buffer: all tcgen05.ld of this warp have completed (wait::ld above)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    if (row < p.nA) {
+      p.part_m[(int64_t)blockIdx.y * p.nA + row] = run_m;
+      p.part_s[(int64_t)blockIdx.y * p.nA + row] = run_s;
+    }
+  }
+  // ---- teardown: everyone done with TMEM before the owner frees it ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// [n, d_pad] fp32 row-major; box = BK elements x box_rows rows, 128-byte swizzle, OOB rows read as zero.
+static int make_map(CUtensorMap* map, const float* base, int64_t n, int d_pad, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return EG_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)n};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EG_OK : EG_ERR_INVALID;
+}
+
+static void pick_grid(int64_t nA, int64_t nB, int* splits, int* tiles_per_split) {
+  int64_t row_tiles = ceil_div(nA, BM);
+  int64_t b_tiles = ceil_div(nB, BN);
+  int64_t want = ceil_div((int64_t)kNumSMs, row_tiles);   // at least one CTA per SM when rows are few
+  if (want > b_tiles) want = b_tiles;
+  if (want < 1) want = 1;
+  int64_t tps = ceil_div(b_tiles, want);
+  *tiles_per_split = (int)tps;
+  *splits = (int)ceil_div(b_tiles, tps);
+}
+
+}  // namespace tc
+
+__global__ void lse_combine_tc_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
+                                      int n_split, int64_t n, const float* __restrict__ logw,
+                                      float* __restrict__ pot_out, float* __restrict__ lse_out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float m = -CUDART_INF_F, s = 0.f;
+  for (int k = 0; k < n_split; ++k) {
+    float om = part_m[(int64_t)k * n + i], os = part_s[(int64_t)k * n + i];
+    float mx = fmaxf(m, om);
+    if (mx > -CUDART_INF_F) { s = s * __expf(m - mx) + os * __expf(om - mx); m = mx; }
+  }
+  float l = s > 0.f ? m + logf(s) : -CUDART_INF_F;
+  if (lse_out) lse_out[i] = l;
+  if (pot_out) pot_out[i] = (logw ? logw[i] : 0.f) - l;
+}
+
+size_t lse_fused_tc_workspace(int64_t nA, int64_t nB, int d) {
+  (void)d;
+  int splits, tps;
+  tc::pick_grid(nA, nB, &splits, &tps);
+  return 2 * align_up(sizeof(float) * (size_t)splits * (size_t)nA);
+}
+
+int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
+                 const float* pot_in, const float* logw, float* pot_out, float* lse_out, const float* A_hi,
+                 const float* A_lo, const float* B_hi, const float* B_lo, void* ws, size_t ws_bytes,
+                 cudaStream_t s) {
+  using namespace tc;
+  // operands come from eg_split_tf32: [n, d_pad] with d_pad = d rounded up to 8; the k-loop runs over
+  // whole 32-element blocks and relies on TMA zero fill past d_pad
+  const int d_pad = (d + 7) / 8 * 8;
+  const int k_blocks = (d_pad + BK - 1) / BK;
+  if (nA >= (1ll << 31) || nB >= (1ll << 31)) return EG_ERR_UNSUPPORTED;
+  if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo) & 15) return EG_ERR_INVALID;
+  if ((d_pad * 4) % 16 != 0) return EG_ERR_INVALID;
+  int splits, tps;
+  pick_grid(nA, nB, &splits, &tps);
+  size_t half = align_up(sizeof(float) * (size_t)splits * (size_t)nA);
+  if (ws_bytes < 2 * half) return EG_ERR_WORKSPACE;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, A_hi, nA, d_pad, BM))) return rc;
+  if ((rc = make_map(&ma_lo, A_lo, nA, d_pad, BM))) return rc;
+  if ((rc = make_map(&mb_hi, B_hi, nB, d_pad, BN))) return rc;
+  if ((rc = make_map(&mb_lo, B_lo, nB, d_pad, BN))) return rc;
+  Params p;
+  p.nA = nA; p.nB = nB; p.k_blocks = k_blocks; p.d_pad = d_pad; p.cost = cost; p.inv_reg = inv_reg;
+  p.normA = normA; p.normB = normB; p.pot_in = pot_in; p.tiles_per_split = tps;
+  p.part_m = reinterpret_cast<float*>(ws);
+  p.part_s = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + half);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)splits);
+  lse_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  EG_LAUNCHED();
+  lse_combine_tc_kernel<<<(unsigned)ceil_div(nA, 256), 256, 0, s>>>(p.part_m, p.part_s, splits, nA, logw, pot_out,
+                                                                    lse_out);
+  EG_LAUNCHED();
+  return EG_OK;
 }
 
 }  // namespace eg

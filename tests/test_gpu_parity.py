@@ -303,8 +303,9 @@ def test_sinkhorn_iteration_golden(golden_dir, dev):
         assert relerr(K32, g["S2_K_" + tag]) < 5e-4   # eps=1e-3 amplifies fp32 cost rounding by 1e3
 
 
+@pytest.mark.parametrize("algo", ["simt", "tcgen05"])
 @pytest.mark.parametrize("cost,reg", [("l2", 0.05), ("sqeuclid", 0.1), ("cos", 0.02)])
-def test_sinkhorn_fused_simt_vs_oracle(cost, reg, dev):
+def test_sinkhorn_fused_vs_oracle(cost, reg, algo, dev):
     from oracle import ea_oracle as orc
     from gnn_mtl_b200.utils.ot_loss import sinkhorn_fused
     torch.manual_seed(7)
@@ -316,9 +317,25 @@ def test_sinkhorn_fused_simt_vs_oracle(cost, reg, dev):
     M = Mfn(X.double(), Y.double())
     P_ref, loss_ref = orc.sinkhorn_scaling(a, b, M, reg, numItermax=40)
     P, loss = sinkhorn_fused(X.to(dev), Y.to(dev), a.to(dev), b.to(dev), reg, numItermax=40, cost=cost,
-                             return_plan=True)
+                             algo=algo, return_plan=True)
     assert relerr(P, P_ref) < REL
     assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < REL
+
+
+@pytest.mark.parametrize("nA,nB,d", [(1, 1, 8), (129, 257, 300), (700, 1300, 128), (2500, 900, 52)])
+def test_fused_lse_tcgen05_matches_fp64(nA, nB, d, dev):
+    """TMA + tcgen05 3xTF32 cost tiles against an fp64 materialised reference, ragged edges included."""
+    from gnn_mtl_b200 import _lib, ops
+    torch.manual_seed(nA)
+    X, Y = torch.randn(nA, d, device=dev) * 0.1, torch.randn(nB, d, device=dev) * 0.1
+    pot = torch.randn(nB, device=dev)
+    lw = torch.randn(nA, device=dev)
+    A = ops.FusedOperand(X, _lib.COST_L2, _lib.ALGO_TCGEN05)
+    B = ops.FusedOperand(Y, _lib.COST_L2, _lib.ALGO_TCGEN05)
+    got_pot, got = ops.lse_fused(A, B, _lib.COST_L2, 25.0, pot, lw, _lib.ALGO_TCGEN05, want_lse=True)
+    ref = torch.logsumexp(pot.double()[None, :] - torch.cdist(X.double(), Y.double()) * 25.0, 1)
+    assert float((got.double() - ref).abs().max()) < 2e-5       # absolute error of a log-sum: 2e-5 ~ 2e-5 relative in P
+    assert float((got_pot.double() - (lw.double() - ref)).abs().max()) < 2e-5
 
 
 def test_wasserstein_loss_as_shipped(golden_dir, dev):
