@@ -3,7 +3,7 @@
 //   lse[i] = log sum_j exp(pot[j] - cost(A_i, B_j) * inv_reg)
 //
 // The 128 x 256 tile of dot products A_i·B_j is produced by tcgen05.mma (kind::tf32)
-// with both operands fed by TMA (cp.async.bulk.tensor, 128-byte swizzle) and the
+// with both operands fed by TMA (cp.async.bulk.tensor, 64-byte swizzle, 4 stages) and the
 // accumulator living in TMEM; fp32 accuracy comes from the 3xTF32 split
 //   a·b ≈ a_hi·b_hi + a_hi·b_lo + a_lo·b_hi      (hi = tf32(x), lo = tf32(x - hi), eg_split_tf32)
 // issued as three MMAs per k-step into the same accumulator.  The epilogue reads
@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eg {
@@ -26,12 +28,14 @@ namespace tc {
 
 constexpr int BM = 128;          // rows of A per tile  (UMMA M)
 constexpr int BN = 256;          // rows of B per tile  (UMMA N)
-constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle atom
+constexpr int BK = 16;           // fp32 elements per k-block = one 64-byte swizzle atom
 constexpr int UK = 8;            // K per tcgen05.mma for tf32
-constexpr int STAGES = 2;
-constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 4;   // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KB
+constexpr int STAGES = 4;        // 4 x 48 KB: ~2300 MMA-cycles of lead time for every TMA load
+constexpr int ROW_BYTES = BK * 4;           // smem row pitch of an operand tile (= swizzle span)
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 8 KB
+constexpr int B_TILE_BYTES = BN * BK * 4;   // 16 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 48 KB
+static_assert(ROW_BYTES == 64 || ROW_BYTES == 128, "operand rows must span one 64- or 128-byte swizzle atom");
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 8 + 256 + 1024;  // + (norm,pot) staging + barriers + align
@@ -67,14 +71,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.
+// K-major operand tile whose rows span exactly one swizzle atom (64 or 128 B): rows are ROW_BYTES
+// apart, 8-row groups 8*ROW_BYTES apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t desc = 0;
   desc |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address  [0,14)
   desc |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major)
-  desc |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  desc |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;   // stride byte offset: one 8-row group
   desc |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  desc |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  desc |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;   // SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return desc;
 }
 
@@ -310,7 +315,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [n, d_pad] fp32 row-major; box = BK elements x box_rows rows, 128-byte swizzle, OOB rows read as zero.
+// [n, d_pad] fp32 row-major; box = BK elements x box_rows rows, swizzle = row span, OOB reads as zero.
 static int make_map(CUtensorMap* map, const float* base, int64_t n, int d_pad, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return EG_ERR_UNSUPPORTED;
@@ -319,18 +324,32 @@ static int make_map(CUtensorMap* map, const float* base, int64_t n, int d_pad, i
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EG_OK : EG_ERR_INVALID;
 }
 
+// Row tiles x column splits: choose the split count whose CTA total best fills whole waves of 148
+// SMs, keeping at least 4 column tiles per CTA so the prologue stays amortised.
 static void pick_grid(int64_t nA, int64_t nB, int* splits, int* tiles_per_split) {
-  int64_t row_tiles = ceil_div(nA, BM);
-  int64_t b_tiles = ceil_div(nB, BN);
-  int64_t want = ceil_div((int64_t)kNumSMs, row_tiles);   // at least one CTA per SM when rows are few
-  if (want > b_tiles) want = b_tiles;
-  if (want < 1) want = 1;
-  int64_t tps = ceil_div(b_tiles, want);
+  const int64_t row_tiles = ceil_div(nA, BM);
+  const int64_t b_tiles = ceil_div(nB, BN);
+  int64_t best_s = 1;
+  double best_eff = -1.0;
+  const int64_t max_s = std::min<int64_t>(b_tiles, 64);
+  for (int64_t sp = 1; sp <= max_s; ++sp) {
+    const int64_t tps = ceil_div(b_tiles, sp);
+    if (sp > 1 && tps < 4) break;
+    const int64_t real_s = ceil_div(b_tiles, tps);
+    const int64_t ctas = row_tiles * real_s;
+    const int64_t waves = ceil_div(ctas, (int64_t)kNumSMs);
+    // useful tile-work over allocated tile-work, with a small penalty per extra split (partials + prologue)
+    const double eff = (double)(row_tiles * b_tiles) / (double)(waves * kNumSMs * tps) - 0.002 * (double)real_s;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = real_s; }
+  }
+  const int64_t tps = ceil_div(b_tiles, best_s);
   *tiles_per_split = (int)tps;
   *splits = (int)ceil_div(b_tiles, tps);
 }
