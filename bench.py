@@ -195,7 +195,7 @@ def run_reference(args):
 
 def run_ours(args):
     import torch.distributed as dist
-    from gnn_mtl_b200 import _lib, ops
+    from gnn_mtl_b200 import _lib, ops, parallel
     from gnn_mtl_b200.adjacency import DeviceAdjacency
     from gnn_mtl_b200.models.models_ea import UEAModel
     from gnn_mtl_b200.synth import make_kg_pair
@@ -249,12 +249,7 @@ def run_ours(args):
         loss = model.get_loss_wassertein(out, data, bsz, numItermax=iters, sample=sample)
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+            parallel.allreduce_grads(params)
         opt.step()
         return loss
 

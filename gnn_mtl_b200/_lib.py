@@ -53,7 +53,8 @@ SIGNATURES = {
     "eg_lse_fused": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eg_split_tf32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "eg_plan_fused": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "eg_plan_fused": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp]),
 }
 
 

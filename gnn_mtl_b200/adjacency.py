@@ -182,7 +182,7 @@ class DeviceAdjacency:
 
 def resolve(adj):
     """Whatever a layer was handed -> DeviceAdjacency (cached on the object)."""
-    if isinstance(adj, DeviceAdjacency):
+    if isinstance(adj, DeviceAdjacency) or getattr(adj, "sharded", False):
         return adj
     cached = getattr(adj, "_eg_adj", None)
     if cached is not None and cached.device == adj.device:

@@ -22,6 +22,9 @@ int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, co
                  const float* A_lo, const float* B_hi, const float* B_lo, void* ws, size_t ws_bytes,
                  cudaStream_t s);
 size_t lse_fused_tc_workspace(int64_t nA, int64_t nB, int d);
+int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
+                  const float* f, const float* g, double* loss, float* row_sum, const float* A_hi,
+                  const float* A_lo, const float* B_hi, const float* B_lo, cudaStream_t s);
 
 constexpr int kFT = 64;    // tile edge
 constexpr int kFK = 16;    // k-chunk
@@ -291,17 +294,24 @@ int eg_lse_fused(int algo, int cost, const float* A, int64_t nA, const float* B,
   return EG_OK;
 }
 
-int eg_plan_fused(int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d, const float* normA,
-                  const float* normB, float inv_reg, const float* f, const float* g, float* P, int64_t ldP,
-                  double* loss, float* row_sum, eg_stream_t stream_) {
+int eg_plan_fused(int algo, int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,
+                  const float* normA, const float* normB, float inv_reg, const float* f, const float* g, float* P,
+                  int64_t ldP, double* loss, float* row_sum, const float* A_hi, const float* A_lo,
+                  const float* B_hi, const float* B_lo, eg_stream_t stream_) {
   using namespace eg;
   if (nA < 0 || nB <= 0 || d <= 0 || cost < 0 || cost > 2) return EG_ERR_INVALID;
   if (P && ldP < nB) return EG_ERR_INVALID;
   if (nA == 0) return EG_OK;
-  if (!A || !B || !normA || !normB || !f || !g) return EG_ERR_INVALID;
+  if (!normA || !normB || !f || !g) return EG_ERR_INVALID;
   cudaStream_t s = as_stream(stream_);
   if (loss) EG_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), s));
   if (row_sum) EG_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * (size_t)nA, s));
+  if (algo == EG_ALGO_TCGEN05) {
+    if (P) return EG_ERR_UNSUPPORTED;   // the plan itself is only ever written by the SIMT path (small sizes)
+    if (!A_hi || !A_lo || !B_hi || !B_lo) return EG_ERR_INVALID;
+    return plan_fused_tc(cost, nA, nB, d, normA, normB, inv_reg, f, g, loss, row_sum, A_hi, A_lo, B_hi, B_lo, s);
+  }
+  if (algo != EG_ALGO_SIMT || !A || !B) return EG_ERR_INVALID;
   int splits = pick_splits(nA, nB);
   int64_t cols_per_split = ceil_div(ceil_div(nB, splits), kFT) * kFT;
   splits = (int)ceil_div(nB, cols_per_split);

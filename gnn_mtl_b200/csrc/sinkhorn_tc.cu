@@ -132,10 +132,16 @@ struct Params {
   const float* normB;
   const float* pot_in;
   int tiles_per_split;     // B tiles handled by one CTA (grid.y = splits)
-  float* part_m;           // [splits, nA]
+  float* part_m;           // [splits, nA]                       (MODE 0)
   float* part_s;
+  const float* pot_a;      // f_i                                 (MODE 1)
+  double* loss;            // sum_ij P_ij * cost_ij               (MODE 1)
+  float* row_sum;          // sum_j P_ij, atomically accumulated  (MODE 1, nullable)
 };
 
+// MODE 0: per-row online log-sum-exp of  pot_in[j] - cost*inv_reg          -> part_m / part_s
+// MODE 1: plan statistics with P_ij = exp(pot_a[i] + pot_in[j] - cost*inv_reg) -> loss, row_sum
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -233,7 +239,9 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int row_in_tile = quad * 32 + lane;
     const int64_t row = i0 + row_in_tile;
     const float na = (row < p.nA) ? p.normA[row] : 0.f;
+    const float fa = (MODE == 1 && row < p.nA) ? p.pot_a[row] : -CUDART_INF_F;
     float run_m = -CUDART_INF_F, run_s = 0.f;
+    double loss_acc = 0.0;
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       const int64_t j0 = (int64_t)(t_begin + t) * BN;
@@ -270,12 +278,27 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           z[c + 1] = fmaf(-cst1, p.inv_reg, info.w);
           zmax = fmaxf(zmax, fmaxf(z[c], z[c + 1]));
         }
-        if (zmax > run_m) { run_s *= __expf(run_m - zmax); run_m = zmax; }
-        if (run_m > -CUDART_INF_F) {
-          float acc = 0.f;
+        if (MODE == 0) {
+          if (zmax > run_m) { run_s *= __expf(run_m - zmax); run_m = zmax; }
+          if (run_m > -CUDART_INF_F) {
+            float acc = 0.f;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc += __expf(z[c] - run_m);
-          run_s += acc;
+            for (int c = 0; c < 32; ++c) acc += __expf(z[c] - run_m);
+            run_s += acc;
+          }
+        } else {
+          // z = g_j - cost*inv_reg  =>  cost = (g_j - z) / inv_reg ;  P = exp(f_i + z)
+          float psum = 0.f, pc = 0.f;
+          const float reg = 1.0f / p.inv_reg;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float pe = __expf(fa + z[c]);                     // 0 on padded rows/columns
+            const float gj = ci[c0 + c].y;
+            psum += pe;
+            pc += (pe > 0.f) ? pe * (gj - z[c]) * reg : 0.f;
+          }
+          run_s += psum;
+          loss_acc += (double)pc;
         }
       }
       // release the accumulator buffer: all tcgen05.ld of this warp have completed (wait::ld above)
@@ -283,9 +306,15 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
-    if (row < p.nA) {
-      p.part_m[(int64_t)blockIdx.y * p.nA + row] = run_m;
-      p.part_s[(int64_t)blockIdx.y * p.nA + row] = run_s;
+    if (MODE == 0) {
+      if (row < p.nA) {
+        p.part_m[(int64_t)blockIdx.y * p.nA + row] = run_m;
+        p.part_s[(int64_t)blockIdx.y * p.nA + row] = run_s;
+      }
+    } else {
+      if (row < p.nA && p.row_sum) atomicAdd(&p.row_sum[row], run_s);
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0 && p.loss) atomicAdd(p.loss, loss_acc);
     }
   }
   // ---- teardown: everyone done with TMEM before the owner frees it ----
@@ -379,43 +408,72 @@ size_t lse_fused_tc_workspace(int64_t nA, int64_t nB, int d) {
   return 2 * align_up(sizeof(float) * (size_t)splits * (size_t)nA);
 }
 
+namespace tc {
+struct Launch {
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  Params p;
+  int splits;
+};
+static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB,
+                   float inv_reg, const float* pot_in, const float* A_hi, const float* A_lo, const float* B_hi,
+                   const float* B_lo) {
+  // operands come from eg_split_tf32: [n, d_pad] with d_pad = d rounded up to 8; the k-loop runs over whole
+  // BK-element blocks and relies on TMA zero fill past d_pad
+  const int d_pad = (d + 7) / 8 * 8;
+  if (nA >= (1ll << 31) || nB >= (1ll << 31)) return EG_ERR_UNSUPPORTED;
+  if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo) & 15) return EG_ERR_INVALID;
+  int rc;
+  if ((rc = make_map(&L->ma_hi, A_hi, nA, d_pad, BM))) return rc;
+  if ((rc = make_map(&L->ma_lo, A_lo, nA, d_pad, BM))) return rc;
+  if ((rc = make_map(&L->mb_hi, B_hi, nB, d_pad, BN))) return rc;
+  if ((rc = make_map(&L->mb_lo, B_lo, nB, d_pad, BN))) return rc;
+  Params& p = L->p;
+  p = Params{};
+  p.nA = nA; p.nB = nB; p.k_blocks = (d_pad + BK - 1) / BK; p.d_pad = d_pad; p.cost = cost; p.inv_reg = inv_reg;
+  p.normA = normA; p.normB = normB; p.pot_in = pot_in;
+  pick_grid(nA, nB, &L->splits, &p.tiles_per_split);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  return EG_OK;
+}
+}  // namespace tc
+
 int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
                  const float* pot_in, const float* logw, float* pot_out, float* lse_out, const float* A_hi,
                  const float* A_lo, const float* B_hi, const float* B_lo, void* ws, size_t ws_bytes,
                  cudaStream_t s) {
   using namespace tc;
-  // operands come from eg_split_tf32: [n, d_pad] with d_pad = d rounded up to 8; the k-loop runs over
-  // whole 32-element blocks and relies on TMA zero fill past d_pad
-  const int d_pad = (d + 7) / 8 * 8;
-  const int k_blocks = (d_pad + BK - 1) / BK;
-  if (nA >= (1ll << 31) || nB >= (1ll << 31)) return EG_ERR_UNSUPPORTED;
-  if (((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo) & 15) return EG_ERR_INVALID;
-  if ((d_pad * 4) % 16 != 0) return EG_ERR_INVALID;
-  int splits, tps;
-  pick_grid(nA, nB, &splits, &tps);
-  size_t half = align_up(sizeof(float) * (size_t)splits * (size_t)nA);
+  Launch L;
+  int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, pot_in, A_hi, A_lo, B_hi, B_lo);
+  if (rc) return rc;
+  size_t half = align_up(sizeof(float) * (size_t)L.splits * (size_t)nA);
   if (ws_bytes < 2 * half) return EG_ERR_WORKSPACE;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc;
-  if ((rc = make_map(&ma_hi, A_hi, nA, d_pad, BM))) return rc;
-  if ((rc = make_map(&ma_lo, A_lo, nA, d_pad, BM))) return rc;
-  if ((rc = make_map(&mb_hi, B_hi, nB, d_pad, BN))) return rc;
-  if ((rc = make_map(&mb_lo, B_lo, nB, d_pad, BN))) return rc;
-  Params p;
-  p.nA = nA; p.nB = nB; p.k_blocks = k_blocks; p.d_pad = d_pad; p.cost = cost; p.inv_reg = inv_reg;
-  p.normA = normA; p.normB = normB; p.pot_in = pot_in; p.tiles_per_split = tps;
-  p.part_m = reinterpret_cast<float*>(ws);
-  p.part_s = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + half);
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
-  dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)splits);
-  lse_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  L.p.part_m = reinterpret_cast<float*>(ws);
+  L.p.part_s = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + half);
+  dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);
+  lse_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.p);
   EG_LAUNCHED();
-  lse_combine_tc_kernel<<<(unsigned)ceil_div(nA, 256), 256, 0, s>>>(p.part_m, p.part_s, splits, nA, logw, pot_out,
-                                                                    lse_out);
+  lse_combine_tc_kernel<<<(unsigned)ceil_div(nA, 256), 256, 0, s>>>(L.p.part_m, L.p.part_s, L.splits, nA, logw,
+                                                                    pot_out, lse_out);
+  EG_LAUNCHED();
+  return EG_OK;
+}
+
+// Plan statistics on the same tiles: *loss = sum P∘cost, row_sum[i] = sum_j P_ij (both pre-zeroed by the caller).
+int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
+                  const float* f, const float* g, double* loss, float* row_sum, const float* A_hi,
+                  const float* A_lo, const float* B_hi, const float* B_lo, cudaStream_t s) {
+  using namespace tc;
+  Launch L;
+  int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, g, A_hi, A_lo, B_hi, B_lo);
+  if (rc) return rc;
+  L.p.pot_a = f; L.p.loss = loss; L.p.row_sum = row_sum;
+  dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);
+  lse_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.p);
   EG_LAUNCHED();
   return EG_OK;
 }

@@ -54,6 +54,8 @@ class _Aggregate(torch.autograd.Function):
     def forward(ctx, hidden, gate_pre, x_res, adjacency, act_code):
         needs_grad = any(ctx.needs_input_grad[:3])
         save_act = needs_grad and (act_code == _lib.ACT_RELU or gate_pre is not None)
+        if getattr(adjacency, "sharded", False):     # row-partitioned graph: fetch every rank's feature rows
+            hidden = adjacency.gather(hidden)
         out, act_out = ops.spmm(adjacency.csr, hidden, act_code, gate_pre, x_res, save_act=save_act)
         ctx.adjacency, ctx.act_code = adjacency, act_code
         ctx.has_gate = gate_pre is not None
@@ -78,6 +80,8 @@ class _Aggregate(torch.autograd.Function):
             dS = dout
         dH = None
         if need_h:
+            if getattr(ctx.adjacency, "sharded", False):
+                dS = ctx.adjacency.gather(dS)
             dH, _ = ops.spmm(ctx.adjacency.csr_t, dS, _lib.ACT_IDENTITY)
         return dH, d_gate, d_xres, None, None
 

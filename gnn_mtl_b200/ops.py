@@ -279,12 +279,15 @@ def lse_fused(A, B, cost, inv_reg, pot_in, logw=None, algo=_lib.ALGO_SIMT, want_
     return pot_out, lse_out
 
 
-def plan_fused(A, B, cost, inv_reg, f, g, want_plan=False, want_rows=True):
+def plan_fused(A, B, cost, inv_reg, f, g, want_plan=False, want_rows=True, algo=_lib.ALGO_SIMT):
     dev = A.X.device
+    if want_plan:
+        algo = _lib.ALGO_SIMT      # only the SIMT tiles write P (small problems)
     P = torch.empty(A.n, B.n, dtype=torch.float32, device=dev) if want_plan else None
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
     rs = torch.empty(A.n, dtype=torch.float32, device=dev) if want_rows else None
     with torch.cuda.device(dev):
-        check(lib.eg_plan_fused(cost, ptr(A.X), A.n, ptr(B.X), B.n, A.d, ptr(A.norm), ptr(B.norm), float(inv_reg),
-                                ptr(f), ptr(g), ptr(P), B.n, ptr(loss), ptr(rs), stream()), "eg_plan_fused")
+        check(lib.eg_plan_fused(algo, cost, ptr(A.X), A.n, ptr(B.X), B.n, A.d, ptr(A.norm), ptr(B.norm),
+                                float(inv_reg), ptr(f), ptr(g), ptr(P), B.n, ptr(loss), ptr(rs),
+                                ptr(A.hi), ptr(A.lo), ptr(B.hi), ptr(B.lo), stream()), "eg_plan_fused")
     return P, loss[0], rs

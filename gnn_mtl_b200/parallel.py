@@ -1,0 +1,204 @@
+"""One-node multi-GPU layer: one process per GPU, torch.distributed (NCCL over
+NVLink/NVSwitch) for the exchanges the path really has.
+
+  * Sinkhorn / eval: source rows are block-partitioned across ranks, the target
+    set is replicated.  Row updates are local.  The column update needs
+    LSE over ALL rows: each rank reduces its own rows with the fused kernel and
+    the [G, J] partial log-sum-exps are all-gathered and combined (one 4·J-byte
+    exchange per sweep).  Eval: diagonal all-gather + one int32 sum of column
+    rank counts.
+  * SpMM: 1-D row partition of A (and of Aᵀ for the backward); feature rows are
+    all-gathered before each aggregation.  Only worth it for graphs beyond one GPU.
+  * Weights are replicated; `allreduce_grads` averages their gradients.
+
+The reference has no distributed code at all (single process), so
+these entry points are additions, not mirrors.  The collective logic is written
+against callables so the world_size-2 gloo tests can drive it on CPU tensors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_range(n, rank, size):
+    """Contiguous block partition with equal ceil(n/size) blocks (last may be short/empty)."""
+    per = -(-n // size)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def all_gather_rows(local, n_total, group=None):
+    """Concatenate equal-size row blocks from every rank ([per, ...] each, padded) -> [n_total, ...]."""
+    rank, size = world(group)
+    if size == 1:
+        return local
+    per = -(-n_total // size)
+    if local.shape[0] != per:
+        pad = torch.zeros((per - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad])
+    out = torch.empty((per * size,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out[:n_total]
+
+
+def combine_partial_lse(local_lse, group=None):
+    """log sum_r exp(lse_r) over ranks: all-gather the [J] partials, reduce the [G, J] stack."""
+    rank, size = world(group)
+    if size == 1:
+        return local_lse
+    flat = local_lse.contiguous().reshape(-1)
+    stack = torch.empty(size * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(stack, flat, group=group)
+    return torch.logsumexp(stack.view(size, -1), dim=0).view(local_lse.shape)
+
+
+def allreduce_grads(params, group=None):
+    """Average parameter gradients over ranks with ONE flat all-reduce (≈1 MB for the EA model)."""
+    rank, size = world(group)
+    params = [p for p in params if p.grad is not None]
+    if size == 1 or not params:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, group=group)
+    flat /= size
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p))
+        off += n
+
+
+# --------------------------------------------------------------------------- Sinkhorn
+
+def sharded_sinkhorn(col_lse_local, row_update_local, n_rows_total, n_cols, log_b, b, n_local, device, dtype,
+                     numItermax=1000, stopThr=1e-9, group=None):
+    """Row-sharded log-domain Sinkhorn (the iteration of utils/ot_loss.py:50-70).
+
+    col_lse_local(log_u_local) -> [J] log-sum-exp over THIS rank's rows
+    row_update_local(log_v)    -> [n_local] new log_u for this rank's rows
+    Returns (log_u_local, log_v, sweeps, err).  Same schedule as the single-GPU
+    solver: column then row per sweep, marginal error from the next column pass
+    on sweeps 0, 10, 20, ….
+    """
+    log_u = torch.full((n_local,), -math.log(n_rows_total), dtype=dtype, device=device)
+    log_v = torch.full((n_cols,), -math.log(n_cols), dtype=dtype, device=device)
+    err, sweeps = 1.0, 0
+    for cpt in range(numItermax):
+        col_lse = combine_partial_lse(col_lse_local(log_u), group)
+        if cpt >= 1 and (cpt - 1) % 10 == 0:
+            err = float(torch.linalg.vector_norm(torch.exp(log_v + col_lse).double() - b.double()))
+            if not err > stopThr:
+                break
+        log_v = log_b - col_lse
+        log_u = row_update_local(log_v)
+        sweeps = cpt + 1
+    return log_u, log_v, sweeps, err
+
+
+def sinkhorn_fused_sharded(X_local, Y, a_local, b, reg, n_rows_total, numItermax=50, stopThr=0.0, cost="l2",
+                           algo="tcgen05", group=None):
+    """Fused (cost never materialised) Sinkhorn with the rows of X sharded over
+    ranks and Y replicated.  Returns (log_u_local, log_v, loss, info)."""
+    from . import _lib, ops
+    cost_id = {"l2": _lib.COST_L2, "sqeuclid": _lib.COST_SQEUCLID, "cos": _lib.COST_COSINE}[cost]
+    algo_id = {"simt": _lib.ALGO_SIMT, "tcgen05": _lib.ALGO_TCGEN05}[algo]
+    A = ops.FusedOperand(X_local.detach(), cost_id, algo_id)
+    B = ops.FusedOperand(Y.detach(), cost_id, algo_id)
+    inv_reg = 1.0 / reg
+    log_a = torch.log(a_local.detach().float()).contiguous()
+    log_b = torch.log(b.detach().float()).contiguous()
+
+    def col_lse_local(log_u):
+        return ops.lse_fused(B, A, cost_id, inv_reg, log_u, None, algo_id, want_pot=False, want_lse=True)[1]
+
+    def row_update_local(log_v):
+        return ops.lse_fused(A, B, cost_id, inv_reg, log_v, log_a, algo_id)[0]
+
+    log_u, log_v, sweeps, err = sharded_sinkhorn(col_lse_local, row_update_local, n_rows_total, B.n, log_b,
+                                                 b.detach().float(), A.n, A.X.device, torch.float32,
+                                                 numItermax, stopThr, group)
+    _, loss, _ = ops.plan_fused(A, B, cost_id, inv_reg, log_u, log_v, want_plan=False, want_rows=False, algo=algo_id)
+    loss = loss.reshape(1).clone()
+    if world(group)[1] > 1:
+        dist.all_reduce(loss, group=group)
+    return log_u, log_v, loss[0], {"sweeps": sweeps, "err": err}
+
+
+# --------------------------------------------------------------------------- eval
+
+def merge_rank_counts(rank_row_local, rank_col_partial, n_total, group=None):
+    """Row ranks are complete per rank (all-gather); column ranks are partial counts (sum)."""
+    rank, size = world(group)
+    if size == 1:
+        return rank_row_local, rank_col_partial
+    rows = all_gather_rows(rank_row_local, n_total, group)
+    cols = rank_col_partial.clone()
+    dist.all_reduce(cols, group=group)
+    return rows, cols
+
+
+def get_hits_sharded(vec, test_pair, top_k=(1, 10, 50, 100), group=None):
+    """utils/eval_utils.py:71-98 with the rows of the L1 matrix split over ranks.
+    Every rank passes the same `vec` / `test_pair` and gets the same dict."""
+    import numpy as np
+    from . import ops
+    from .utils.eval_utils import _hits_dict, _pair_index, _to_cuda
+    rank, size = world(group)
+    vec = _to_cuda(vec.detach())
+    left, right = _pair_index(test_pair, vec.device)
+    n = int(left.numel())
+    r0, r1 = shard_range(n, rank, size)
+    R = vec.index_select(0, right).float()
+    L_loc = vec.index_select(0, left[r0:r1]).float()
+    diag_loc = ops.l1_paired(L_loc, R[r0:r1])
+    diag = all_gather_rows(diag_loc, n, group)
+    rank_row = torch.zeros(n, dtype=torch.int32, device=vec.device)
+    rank_col = torch.zeros(n, dtype=torch.int32, device=vec.device)
+    rows = ops.l1_block_rows(n)
+    if r1 > r0:
+        buf = torch.empty(min(rows, r1 - r0), n, dtype=torch.float64, device=vec.device)
+        for s0 in range(r0, r1, rows):
+            s1 = min(r1, s0 + rows)
+            D = ops.l1_matrix(L_loc[s0 - r0:s1 - r0], R, out=buf[:s1 - s0])
+            ops.rank_accumulate(D, s0, diag, rank_row, rank_col)
+    rank_row, rank_col = merge_rank_counts(rank_row[r0:r1], rank_col, n, group)
+    return _hits_dict(rank_row, rank_col, top_k, n)
+
+
+# --------------------------------------------------------------------------- SpMM
+
+class ShardedAdjacency:
+    """Row block [r0, r1) of A and of Aᵀ (kernel-format CSR, full column range).
+    `gather` all-gathers the feature rows every aggregation needs."""
+
+    sharded = True
+
+    def __init__(self, full, group=None):
+        from .adjacency import _Csr
+        self.group = group
+        self.rank, self.size = world(group)
+        self.n = full.n
+        self.r0, self.r1 = shard_range(full.n, self.rank, self.size)
+        self.csr = self._slice(full.csr, _Csr)
+        self.csr_t = self._slice(full.csr_t, _Csr)
+        self.device = full.device
+
+    def _slice(self, c, _Csr):
+        e0, e1 = int(c.rowptr[self.r0]), int(c.rowptr[self.r1])
+        rowptr = (c.rowptr[self.r0:self.r1 + 1] - e0).contiguous()
+        return _Csr(self.r1 - self.r0, c.n_cols, rowptr, c.col[e0:e1].clone(), c.val[e0:e1].clone(), c.threshold)
+
+    def gather(self, local_rows):
+        return all_gather_rows(local_rows, self.n, self.group)
+
+    def local(self, full_rows):
+        return full_rows[self.r0:self.r1]

@@ -44,7 +44,7 @@ def sinkhorn(a, b, M, reg, numItermax=1000, stopThr=1e-9, verbose=False, *, retu
     return (P.to(torch.float64) if P is not None else None), loss
 
 
-def sinkhorn_fused(X, Y, a, b, reg, numItermax=1000, stopThr=1e-9, cost="l2", algo="simt",
+def sinkhorn_fused(X, Y, a, b, reg, numItermax=1000, stopThr=1e-9, cost="l2", algo="tcgen05",
                    return_plan=False, info=None):
     """Same solver with the cost recomputed tile by tile from the embeddings
     (models/models_ea.py:218 fused into utils/ot_loss.py:53-55); the I×J cost is
@@ -73,7 +73,8 @@ def sinkhorn_fused(X, Y, a, b, reg, numItermax=1000, stopThr=1e-9, cost="l2", al
         log_v = new_v
         log_u, _ = ops.lse_fused(A, B, cost_id, inv_reg, log_v, log_a, algo_id)
         sweeps = cpt + 1
-    P, loss, _ = ops.plan_fused(A, B, cost_id, inv_reg, log_u, log_v, want_plan=return_plan, want_rows=False)
+    P, loss, _ = ops.plan_fused(A, B, cost_id, inv_reg, log_u, log_v, want_plan=return_plan, want_rows=False,
+                                algo=algo_id)
     if info is not None:
         info.update(sweeps=sweeps, err=err, log_u=log_u, log_v=log_v)
     return P, loss

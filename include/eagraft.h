@@ -181,10 +181,12 @@ size_t eg_lse_fused_workspace_bytes(int algo, int64_t nA, int64_t nB, int d);
 int eg_split_tf32(const float* X, int64_t n, int d, int d_pad, float* hi, float* lo, eg_stream_t stream);
 /* Fused plan statistics: *loss = sum_ij P_ij * cost_ij with P = exp(f_i + g_j - cost*inv_reg);
  * row_sum[i] (nullable) = sum_j P_ij (both zeroed by the call).  P (nullable) [nA, ldP]
- * is written only on request. */
-int eg_plan_fused(int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,
+ * is written only on request and only by EG_ALGO_SIMT; EG_ALGO_TCGEN05 takes the
+ * split operands like eg_lse_fused. */
+int eg_plan_fused(int algo, int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,
                   const float* normA, const float* normB, float inv_reg,
                   const float* f, const float* g, float* P, int64_t ldP, double* loss, float* row_sum,
+                  const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
                   eg_stream_t stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,150 @@
+"""CPU, world_size 2, gloo: the collective logic of gnn_mtl_b200/parallel.py driven by
+torch-CPU stand-ins for the per-rank kernels (the kernels themselves are covered by -m gpu)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run(fn, world=2):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    results = [q.get() for _ in range(world)]
+    for r in results:
+        assert r == "ok", r
+
+
+def _entry(fn, rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        torch.set_num_threads(1)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        fn(rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put("ok")
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put("rank %d: %s\n%s" % (rank, e, traceback.format_exc()))
+
+
+def _w_sinkhorn(rank, world):
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import parallel as par
+    torch.manual_seed(0)
+    I, J = 37, 29                       # uneven split: 19 + 18 rows
+    X, Y = torch.randn(I, 6).double() * 0.3, torch.randn(J, 6).double() * 0.3
+    a = torch.rand(I).double() + 0.5
+    b = torch.rand(J).double() + 0.5
+    b = b * a.sum() / b.sum()
+    M = torch.cdist(X, Y)
+    reg = 0.2
+    r0, r1 = par.shard_range(I, rank, world)
+    Ml = M[r0:r1]
+
+    def col_lse_local(log_u):
+        return torch.logsumexp(log_u[:, None] - Ml / reg, 0)
+
+    def row_update_local(log_v):
+        return torch.log(a[r0:r1]) - torch.logsumexp(log_v[None, :] - Ml / reg, 1)
+
+    for thr, iters in ((1e-9, 23), (1e-4, 1000)):
+        lu, lv, sweeps, err = par.sharded_sinkhorn(col_lse_local, row_update_local, I, J, torch.log(b), b, r1 - r0,
+                                                   "cpu", torch.float64, numItermax=iters, stopThr=thr)
+        P_ref, _, info = orc.sinkhorn_scaling(a, b, M, reg, numItermax=iters, stopThr=thr, return_info=True)
+        assert sweeps == info["sweeps"], (sweeps, info["sweeps"])
+        P_loc = torch.exp(lu[:, None] + lv[None, :] - Ml / reg)
+        assert torch.allclose(P_loc, P_ref[r0:r1], rtol=1e-9, atol=1e-14)
+
+
+def _w_gather_and_grads(rank, world):
+    from gnn_mtl_b200 import parallel as par
+    n = 7
+    r0, r1 = par.shard_range(n, rank, world)
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+    got = par.all_gather_rows(full[r0:r1], n)
+    assert torch.equal(got, full)
+    lse = par.combine_partial_lse(torch.tensor([0.0 + rank, 1.0, -float("inf")]))
+    want = torch.logsumexp(torch.tensor([[0.0, 1.0, -float("inf")], [1.0, 1.0, -float("inf")]]), 0)
+    assert torch.allclose(lse[:2], want[:2]) and lse[2] == -float("inf")
+    lin = torch.nn.Linear(4, 3)
+    lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+    lin.bias.grad = torch.full_like(lin.bias, float(10 * (rank + 1)))
+    par.allreduce_grads(lin.parameters())
+    assert torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 1.5))
+    assert torch.allclose(lin.bias.grad, torch.full_like(lin.bias, 15.0))
+
+
+def _w_rank_merge(rank, world):
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import parallel as par
+    rng = np.random.default_rng(3)
+    n = 41
+    L = rng.standard_normal((n, 5)).astype(np.float32)
+    R = L + 0.7 * rng.standard_normal((n, 5)).astype(np.float32)
+    sim = orc.l1_matrix(L, R)
+    rr, cr = orc.diagonal_ranks(sim)
+    r0, r1 = par.shard_range(n, rank, world)
+    diag = np.diag(sim)
+    blk = sim[r0:r1]
+    gi = np.arange(r0, r1)
+    row_local = ((blk < diag[gi, None]).sum(1) + ((blk == diag[gi, None]) & (np.arange(n)[None, :] < gi[:, None])).sum(1))
+    col_part = ((blk < diag[None, :]).sum(0) + ((blk == diag[None, :]) & (gi[:, None] < np.arange(n)[None, :])).sum(0))
+    rows, cols = par.merge_rank_counts(torch.from_numpy(row_local.astype(np.int32)),
+                                       torch.from_numpy(col_part.astype(np.int32)), n)
+    assert np.array_equal(rows.numpy(), rr) and np.array_equal(cols.numpy(), cr)
+
+
+def _w_sharded_adjacency(rank, world):
+    import scipy.sparse as sp
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import parallel as par
+    from gnn_mtl_b200.adjacency import _Csr
+    rng = np.random.default_rng(1)
+    n = 53
+    h, t = rng.integers(0, n, 300), rng.integers(0, n, 300)
+    crow, col, val = orc.adjacency_csr(n, h, t)
+    A = sp.csr_matrix((val, col, crow), shape=(n, n))
+    At = A.T.tocsr(); At.sort_indices()
+
+    class _Full:
+        pass
+    full = _Full()
+    full.n, full.device = n, torch.device("cpu")
+    full.csr = _Csr(n, n, torch.from_numpy(crow.astype(np.int32)), torch.from_numpy(col.astype(np.int32)),
+                    torch.from_numpy(val), threshold=4)
+    full.csr_t = _Csr(n, n, torch.from_numpy(At.indptr.astype(np.int32)), torch.from_numpy(At.indices.astype(np.int32)),
+                      torch.from_numpy(At.data.astype(np.float32)), threshold=4)
+    sh = par.ShardedAdjacency(full)
+    H = torch.from_numpy(rng.standard_normal((n, 4)).astype(np.float32))
+    Hg = sh.gather(sh.local(H))
+    assert torch.equal(Hg, H)
+    c = sh.csr
+    loc = sp.csr_matrix((c.val.numpy(), c.col.numpy(), c.rowptr.numpy()), shape=(c.n_rows, n))
+    assert np.allclose(loc @ H.numpy(), (A @ H.numpy())[sh.r0:sh.r1])
+    # hub segmentation indices are local to the slice
+    if c.n_seg:
+        assert int(c.seg_begin.min()) >= 0 and int(c.seg_end.max()) <= c.nnz
+
+
+@pytest.mark.parametrize("worker", [_w_sinkhorn, _w_gather_and_grads, _w_rank_merge, _w_sharded_adjacency])
+def test_world2_gloo(worker):
+    _run(worker, 2)
