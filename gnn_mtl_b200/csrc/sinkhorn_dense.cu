@@ -11,6 +11,10 @@
 // arithmetic to rounding.
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eg {
@@ -32,22 +36,27 @@ template <typename T>
 struct Lse {
   T m, s;
   __device__ __forceinline__ void init() { m = Num<T>::ninf(); s = T(0); }
+  // Branch-free (the solver kernels are instruction-issue bound; divergent `if (z > m)` costs more than one
+  // extra exp): new max, rescale the running sum, add the four terms.  -inf inputs contribute exp(-inf) = 0;
+  // an all -inf state keeps m = -inf, s = 0 (the reference point is clamped so that -inf - ref stays -inf).
   __device__ __forceinline__ void push4(T z0, T z1, T z2, T z3) {
-    T mx = fmax(fmax(z0, z1), fmax(z2, z3));
-    if (mx > m) { s *= Num<T>::exp_(m - mx); m = mx; }   // exp(-inf) = 0 on the first push
-    if (m > Num<T>::ninf())
-      s += Num<T>::exp_(z0 - m) + Num<T>::exp_(z1 - m) + Num<T>::exp_(z2 - m) + Num<T>::exp_(z3 - m);
+    const T mx = fmax(fmax(fmax(z0, z1), fmax(z2, z3)), m);
+    const T ref = (mx == Num<T>::ninf()) ? T(0) : mx;
+    s = s * Num<T>::exp_(m - ref) +
+        ((Num<T>::exp_(z0 - ref) + Num<T>::exp_(z1 - ref)) + (Num<T>::exp_(z2 - ref) + Num<T>::exp_(z3 - ref)));
+    m = mx;
   }
   __device__ __forceinline__ void push1(T z) {
-    if (z > m) { s *= Num<T>::exp_(m - z); m = z; }
-    if (m > Num<T>::ninf()) s += Num<T>::exp_(z - m);
+    const T mx = fmax(z, m);
+    const T ref = (mx == Num<T>::ninf()) ? T(0) : mx;
+    s = s * Num<T>::exp_(m - ref) + Num<T>::exp_(z - ref);
+    m = mx;
   }
   __device__ __forceinline__ void merge(T om, T os) {
-    T mx = fmax(m, om);
-    if (mx > Num<T>::ninf()) {
-      s = s * Num<T>::exp_(m - mx) + os * Num<T>::exp_(om - mx);
-      m = mx;
-    }
+    const T mx = fmax(m, om);
+    const T ref = (mx == Num<T>::ninf()) ? T(0) : mx;
+    s = s * Num<T>::exp_(m - ref) + os * Num<T>::exp_(om - ref);
+    m = mx;
   }
   __device__ __forceinline__ T value() const { return (s > T(0)) ? m + Num<T>::log_(s) : Num<T>::ninf(); }
 };
@@ -281,10 +290,268 @@ static int plan_t(const T* M, int64_t n_rows, int64_t n_cols, int64_t ld, double
   return EG_OK;
 }
 
+
+// ---- whole solve in ONE persistent cooperative kernel -----------------------------------------
+// The streaming path above costs a launch (and a cold start) per half-sweep: 2000 launches for the
+// reference's default 1000 sweeps.  Here one CTA per SM owns a contiguous block of rows for the whole
+// solve; per sweep
+//   C: partial column log-sum-exp over the CTA's rows           (thread = 16-byte column group)
+//   -- grid barrier --
+//   R: CTA c merges the partials of its slice of columns -> log v (+ marginal error on check sweeps)
+//   -- grid barrier --
+//   U: row update for the CTA's rows against the new log v      (warp = row)
+// so M is read twice per sweep (from L2 when it fits), nothing else leaves the SM, and the only
+// global synchronisation is two barriers per sweep.  Same init, order and stopping rule as
+// utils/ot_loss.py:38-70.
+
+struct PersistState {
+  unsigned int barrier;      // monotonically increasing arrival counter
+  int sweeps;                // sweeps completed (host output)
+  int final_buf;             // which log-v buffer holds the accepted iterate
+  double err;                // last marginal error evaluated
+  double err2[128];          // one accumulator per check (sweeps 0,10,...)
+  unsigned long long t_phase[8];   // ns spent by CTA 0 in C, barrier, R, barrier, U (diagnostic)
+};
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblocks) {
+  __syncthreads();   // all of this CTA's writes are ordered before thread 0's release below (CTA-scope barrier)
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+__device__ __forceinline__ void unpack(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+
+constexpr int kPersistThreads = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+sinkhorn_persistent_kernel(const T* __restrict__ M, int64_t I, int64_t J, int64_t ld, T inv_reg,
+                           const T* __restrict__ log_a, const T* __restrict__ log_b, const T* __restrict__ b,
+                           int max_iter, double stop_thr, T* __restrict__ part_m, T* __restrict__ part_s,
+                           T* __restrict__ lv_buf /* [2][J] */, T* __restrict__ log_u_out, T* __restrict__ log_v_out,
+                           PersistState* __restrict__ st, int rows_resident) {
+  using Vec = typename VecOf<T>::type;
+  constexpr int V = VecOf<T>::N;
+  constexpr int kWarps = kPersistThreads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw_p[];
+  const int nb = gridDim.x, cta = blockIdx.x;
+  const int64_t rows_per = (I + nb - 1) / nb;
+  const int64_t row0 = min(I, (int64_t)cta * rows_per);
+  const int R = (int)(min(I, row0 + rows_per) - row0);
+  const int64_t cols_per = (J + nb - 1) / nb;
+  const int64_t col0 = min(J, (int64_t)cta * cols_per), col1 = min(J, col0 + cols_per);
+  // shared memory: log v [J] | my log u [rows_per] | cross-warp merge scratch [2][kWarps][32] | resident rows of M
+  T* lv_s = reinterpret_cast<T*>(smem_raw_p);
+  T* lu_s = lv_s + J;
+  T* red_m = lu_s + ((rows_per + 3) / 4) * 4;
+  T* red_s = red_m + kWarps * 32;
+  Vec* m_res = reinterpret_cast<Vec*>(red_s + kWarps * 32);          // [S][J / V], 16-byte aligned by construction
+  const int S = min(R, rows_resident);
+  __shared__ double err_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t groups = J / V;                                       // J % V == 0 is a launch precondition
+  const int64_t ldv = ld / V;
+  unsigned int target = 0;
+
+  for (int r = tid; r < R; r += kPersistThreads) lu_s[r] = (T)(-log((double)I));
+  // rows [0, S) of my block stay in shared memory for the whole solve; the rest stream from L2 every phase
+  for (int r = 0; r < S; ++r) {
+    const Vec* src = reinterpret_cast<const Vec*>(M + (row0 + r) * ld);
+    for (int64_t g = tid; g < groups; g += kPersistThreads) m_res[(int64_t)r * groups + g] = src[g];
+  }
+  __syncthreads();
+
+  int cpt = 0, sweeps = 0, final_buf = 0;
+  double err = 1.0;
+  bool stopped = false;
+  const bool timer = (cta == 0 && tid == 0);
+  for (cpt = 0; cpt < max_iter; ++cpt) {
+    const int cur = cpt & 1, nxt = cur ^ 1;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    if (timer) t0 = gtime();
+    // ---- C: partial column LSE over my rows (thread = 16-byte column group, V independent chains) -----
+    const int ngroups = (int)groups;
+    for (int g = tid; g < ngroups; g += kPersistThreads) {
+      Lse<T> acc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v].init();
+      const Vec* gbase = reinterpret_cast<const Vec*>(M + row0 * ld) + g;
+      const Vec* sbase = m_res + g;
+      for (int r0 = 0; r0 < R; r0 += 4) {
+        Vec mv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          mv[u] = (r < S) ? sbase[r * ngroups] : (r < R ? gbase[(int64_t)r * ldv] : Vec());
+        }
+        T z[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T lu = (r0 + u < R) ? lu_s[r0 + u] : Num<T>::ninf();
+          T e[V];
+          unpack(mv[u], e);
+#pragma unroll
+          for (int v = 0; v < V; ++v) z[u][v] = lu - e[v] * inv_reg;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v].push4(z[0][v], z[1][v], z[2][v], z[3][v]);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        part_m[(int64_t)cta * J + (int64_t)g * V + v] = acc[v].m;
+        part_s[(int64_t)cta * J + (int64_t)g * V + v] = acc[v].s;
+      }
+    }
+    if (timer) t1 = gtime();
+    grid_barrier(&st->barrier, target, nb);
+    if (timer) t2 = gtime();
+    // ---- R: merge all CTAs' partials for my slice of columns -> log v --------------------------------
+    // lane = column inside the slice (contiguous floats: coalesced), warp = strided subset of source CTAs
+    const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
+    const int slot = check ? ((cpt - 1) / 10) & 127 : 0;
+    if (tid == 0) err_s = 0.0;
+    for (int64_t c0 = col0; c0 < col1; c0 += 32) {
+      const int64_t j = c0 + lane;
+      Lse<T> acc;
+      acc.init();
+      if (j < col1) {
+        // values written by other SMs since this SM last read them: read at L2, not a stale L1 line
+        T pm[5], ps[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int pidx = warp + kWarps * k;
+          pm[k] = (pidx < nb) ? __ldcg(part_m + (int64_t)pidx * J + j) : Num<T>::ninf();
+          ps[k] = (pidx < nb) ? __ldcg(part_s + (int64_t)pidx * J + j) : T(0);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc.merge(pm[k], ps[k]);
+        for (int pidx = warp + kWarps * 5; pidx < nb; pidx += kWarps)
+          acc.merge(__ldcg(part_m + (int64_t)pidx * J + j), __ldcg(part_s + (int64_t)pidx * J + j));
+      }
+      red_m[warp * 32 + lane] = acc.m;
+      red_s[warp * 32 + lane] = acc.s;
+      __syncthreads();
+      {
+        // warp w finishes column c0 + w: lanes hold the 32 per-warp partials, 5 shuffle-merge steps
+        const int64_t jc = c0 + warp;
+        Lse<T> tot;
+        tot.m = red_m[lane * 32 + warp];
+        tot.s = red_s[lane * 32 + warp];
+        warp_merge(tot);
+        if (lane == 0 && jc < col1) {
+          const T lse = tot.value();
+          if (check) {
+            const double d = (double)Num<T>::exp_(__ldcg(lv_buf + (int64_t)cur * J + jc) + lse) - (double)b[jc];
+            atomicAdd(&err_s, d * d);
+          }
+          lv_buf[(int64_t)nxt * J + jc] = log_b[jc] - lse;
+        }
+      }
+      __syncthreads();
+    }
+    if (check && tid == 0 && err_s != 0.0) atomicAdd(&st->err2[slot], err_s);
+    if (timer) t3 = gtime();
+    grid_barrier(&st->barrier, target, nb);
+    if (timer) t4 = gtime();
+    if (check) {
+      double e2;
+      asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(e2) : "l"(&st->err2[slot]) : "memory");
+      err = sqrt(e2);
+      if (!(err > stop_thr)) { stopped = true; final_buf = cur; break; }   // sweep cpt never happened
+    }
+    // ---- U: row update for my rows with the new log v (warp = row, 4 independent chains per lane) --------
+    {
+      const T* src = lv_buf + (int64_t)nxt * J;
+      for (int64_t j0 = tid; j0 < J; j0 += (int64_t)kPersistThreads * 4) {
+        T val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t j = j0 + (int64_t)u * kPersistThreads;
+          val[u] = (j < J) ? __ldcg(src + j) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t j = j0 + (int64_t)u * kPersistThreads;
+          if (j < J) lv_s[j] = val[u];
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const Vec* pv = reinterpret_cast<const Vec*>(lv_s);
+      for (int r = warp; r < R; r += kWarps) {
+        const Vec* mrow = (r < S) ? (m_res + (int64_t)r * groups) : reinterpret_cast<const Vec*>(M + (row0 + r) * ld);
+        Lse<T> acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u].init();
+        const int ng = (int)groups;
+        for (int g0 = lane; g0 < ng; g0 += 32 * 4) {
+          Vec mv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int g = g0 + 32 * u;
+            mv[u] = (g < ng) ? mrow[g] : Vec();
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int g = g0 + 32 * u;
+            if (g < ng) {
+              T e[V], l[V];
+              unpack(mv[u], e);
+              unpack(pv[g], l);
+              if constexpr (V == 4)
+                acc[u].push4(l[0] - e[0] * inv_reg, l[1] - e[1] * inv_reg, l[2] - e[2] * inv_reg, l[3] - e[3] * inv_reg);
+              else {
+                acc[u].push1(l[0] - e[0] * inv_reg);
+                acc[u].push1(l[1] - e[1] * inv_reg);
+              }
+            }
+          }
+        }
+        acc[0].merge(acc[1].m, acc[1].s);
+        acc[2].merge(acc[3].m, acc[3].s);
+        acc[0].merge(acc[2].m, acc[2].s);
+        warp_merge(acc[0]);
+        if (lane == 0) lu_s[r] = log_a[row0 + r] - acc[0].value();
+      }
+    }
+    __syncthreads();
+    sweeps = cpt + 1;
+    if (timer) {
+      st->t_phase[0] += t1 - t0; st->t_phase[1] += t2 - t1; st->t_phase[2] += t3 - t2;
+      st->t_phase[3] += t4 - t3; st->t_phase[4] += gtime() - t4;
+    }
+  }
+  if (!stopped) final_buf = max_iter & 1;
+  // ---- outputs ---------------------------------------------------------------------------------
+  for (int r = tid; r < R; r += kPersistThreads) log_u_out[row0 + r] = lu_s[r];
+  for (int64_t j = col0 + tid; j < col1; j += kPersistThreads) log_v_out[j] = __ldcg(lv_buf + (int64_t)final_buf * J + j);
+  if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = final_buf; st->err = err; }
+}
+
 template <typename T>
 struct SolveWs {
   T *log_a, *log_b, *lv_alt, *col_lse;
   double* err2;
+  T *part_m, *part_s, *lv_buf;     // persistent-kernel scratch: [SMs, J] x2, [2, J]
+  PersistState* state;
   size_t total;
 };
 template <typename T>
@@ -298,8 +565,71 @@ static SolveWs<T> carve_solve(void* ws, int64_t I, int64_t J) {
   w.lv_alt = (T*)take(sizeof(T) * (size_t)J);
   w.col_lse = (T*)take(sizeof(T) * (size_t)J);
   w.err2 = (double*)take(sizeof(double));
+  w.part_m = (T*)take(sizeof(T) * (size_t)kNumSMs * (size_t)J);
+  w.part_s = (T*)take(sizeof(T) * (size_t)kNumSMs * (size_t)J);
+  w.lv_buf = (T*)take(sizeof(T) * 2 * (size_t)J);
+  w.state = (PersistState*)take(sizeof(PersistState));
   w.total = off;
   return w;
+}
+
+int g_tune_persistent = 1;   // eg_debug_set(3, 0) forces the streaming path
+int g_tune_resident = 1;     // eg_debug_set(4, 0) keeps no rows of M in shared memory
+
+// One cooperative launch for the whole solve when the shape allows it.
+template <typename T>
+static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, const T* a, const T* b, int max_iter,
+                                 double stop_thr, T* log_u, T* log_v, SolveWs<T>& w, int* h_sweeps, double* h_err,
+                                 cudaStream_t s, bool* used) {
+  *used = false;
+  constexpr int V = VecOf<T>::N;
+  if (!g_tune_persistent || J % V != 0 || (reinterpret_cast<uintptr_t>(M) & 15) || max_iter > 1270) return EG_OK;
+  int dev = 0, coop = 0, sms = 0;
+  EG_CUDA(cudaGetDevice(&dev));
+  EG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  EG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!coop || sms > kNumSMs) return EG_OK;
+  const int64_t rows_per = ceil_div(I, (int64_t)sms);
+  const size_t fixed = sizeof(T) * (size_t)(J + (rows_per + 3) / 4 * 4 + 2 * 32 * (kPersistThreads / 32)) + 16;
+  if (fixed > 160 * 1024) return EG_OK;
+  int max_smem = 0;
+  EG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // as many rows of the CTA's block as fit stay resident in shared memory for the whole solve
+  int rows_resident = (int)std::min<int64_t>(rows_per, ((int64_t)max_smem - 1024 - (int64_t)fixed) /
+                                                         (int64_t)(sizeof(T) * (size_t)J));
+  if (rows_resident < 0 || !g_tune_resident) rows_resident = 0;
+  const size_t smem = fixed + sizeof(T) * (size_t)J * (size_t)rows_resident;
+  auto kern = sinkhorn_persistent_kernel<T>;
+  EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  EG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPersistThreads, smem));
+  if (per_sm < 1) return EG_OK;
+  const int TB = 256;
+  log_kernel<T><<<(unsigned)ceil_div(I, TB), TB, 0, s>>>(a, I, w.log_a); EG_LAUNCHED();
+  log_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(b, J, w.log_b); EG_LAUNCHED();
+  fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log((double)J))); EG_LAUNCHED();
+  EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
+  T inv_reg = (T)(1.0 / reg);
+  int64_t ld = J;
+  void* args[] = {(void*)&M, (void*)&I, (void*)&J, (void*)&ld, (void*)&inv_reg, (void*)&w.log_a, (void*)&w.log_b,
+                  (void*)&b, (void*)&max_iter, (void*)&stop_thr, (void*)&w.part_m, (void*)&w.part_s,
+                  (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&w.state, (void*)&rows_resident};
+  EG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)sms), dim3(kPersistThreads), args, smem, s));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  PersistState host_state;
+  EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(int) * 3 + sizeof(double) + 4, cudaMemcpyDeviceToHost, s));
+  EG_CUDA(cudaStreamSynchronize(s));
+  if (h_sweeps) *h_sweeps = host_state.sweeps;
+  if (h_err) *h_err = host_state.err;
+  if (getenv("EG_PERSIST_TIMING")) {
+    PersistState full;
+    cudaMemcpy(&full, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[eagraft] persistent sinkhorn: %d sweeps; CTA0 us/sweep: C %.2f | bar %.2f | R %.2f | bar %.2f | U %.2f\n",
+            full.sweeps, full.t_phase[0] / 1e3 / full.sweeps, full.t_phase[1] / 1e3 / full.sweeps,
+            full.t_phase[2] / 1e3 / full.sweeps, full.t_phase[3] / 1e3 / full.sweeps, full.t_phase[4] / 1e3 / full.sweeps);
+  }
+  *used = true;
+  return EG_OK;
 }
 
 template <typename T>
@@ -308,6 +638,13 @@ static int sinkhorn_dense_t(const T* M, int64_t I, int64_t J, double reg, const 
                             double* h_err, cudaStream_t s) {
   SolveWs<T> w = carve_solve<T>(ws, I, J);
   if (ws_bytes < w.total) return EG_ERR_WORKSPACE;
+  {
+    bool used = false;
+    int prc = sinkhorn_persistent_t<T>(M, I, J, reg, a, b, max_iter, stop_thr, log_u, log_v, w, h_sweeps, h_err, s,
+                                       &used);
+    if (prc) return prc;
+    if (used) return EG_OK;
+  }
   const double inv_reg = 1.0 / reg;
   const int TB = 256;
   int rc = transpose_t<T>(M, I, J, J, Mt, I, s);

@@ -18,6 +18,8 @@ constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
 // Tuning knobs (defaults chosen from the ncu study in profiles/); eg_debug_set() overrides them.
 int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each)
 int g_tune_warps = 4;       // warps (= rows) per CTA
+extern int g_tune_persistent;
+extern int g_tune_resident;
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
 
 struct Epilogue {
@@ -298,6 +300,8 @@ int eg_debug_set(int key, int value) {
   if (key == 0) eg::g_tune_unroll = value;
   else if (key == 1) eg::g_tune_warps = value;
   else if (key == 2) eg::g_tune_hints = value;
+  else if (key == 3) eg::g_tune_persistent = value;
+  else if (key == 4) eg::g_tune_resident = value;
   else return EG_ERR_INVALID;
   return EG_OK;
 }
