@@ -55,6 +55,8 @@ SIGNATURES = {
     "eg_split_tf32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "eg_plan_fused": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp]),
+    "eg_gemm_nt_3xtf32": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp,
+                                    _i64, _vp]),
 }
 
 

@@ -137,14 +137,20 @@ struct Params {
   const float* pot_a;      // f_i                                 (MODE 1)
   double* loss;            // sum_ij P_ij * cost_ij               (MODE 1)
   float* row_sum;          // sum_j P_ij, atomically accumulated  (MODE 1, nullable)
+  int kb_split;            // k-blocks taken from the first A operand; the rest come from A2 (MODE 2: A = [A1 | A2])
+  float* out1;             // C[:, 0:n1)   row stride ld1          (MODE 2)
+  float* out2;             // C[:, n1:nB)  row stride ld2          (MODE 2, nullable)
+  int64_t ld1, ld2, n1;
 };
 
 // MODE 0: per-row online log-sum-exp of  pot_in[j] - cost*inv_reg          -> part_m / part_s
 // MODE 1: plan statistics with P_ij = exp(pot_a[i] + pot_in[j] - cost*inv_reg) -> loss, row_sum
+// MODE 2: plain 3xTF32 GEMM  C = [A1 | A2] · Bᵀ + bias  (pot_in carries the bias)   -> out1 / out2
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
               const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -189,8 +195,13 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = stage_base + s * STAGE_BYTES;
           mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(st, &map_a_hi, &full[s], kb * BK, (int)i0);
-          tma_load_2d(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, (int)i0);
+          if (MODE != 2 || kb < p.kb_split) {
+            tma_load_2d(st, &map_a_hi, &full[s], kb * BK, (int)i0);
+            tma_load_2d(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, (int)i0);
+          } else {
+            tma_load_2d(st, &map_a2_hi, &full[s], (kb - p.kb_split) * BK, (int)i0);
+            tma_load_2d(st + A_TILE_BYTES, &map_a2_lo, &full[s], (kb - p.kb_split) * BK, (int)i0);
+          }
           tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full[s], kb * BK, j0);
           tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[s], kb * BK, j0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -238,7 +249,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;
     const int64_t row = i0 + row_in_tile;
-    const float na = (row < p.nA) ? p.normA[row] : 0.f;
+    const float na = (MODE != 2 && row < p.nA) ? p.normA[row] : 0.f;
     const float fa = (MODE == 1 && row < p.nA) ? p.pot_a[row] : -CUDART_INF_F;
     float run_m = -CUDART_INF_F, run_s = 0.f;
     double loss_acc = 0.0;
@@ -249,7 +260,10 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       float2* ci = colinfo + buf * BN;
       for (int c = ep_tid; c < BN; c += 128) {
         int64_t j = j0 + c;
-        ci[c] = (j < p.nB) ? make_float2(p.normB[j], p.pot_in[j]) : make_float2(0.f, -CUDART_INF_F);
+        if (MODE == 2)
+          ci[c] = make_float2(0.f, (j < p.nB && p.pot_in) ? p.pot_in[j] : 0.f);
+        else
+          ci[c] = (j < p.nB) ? make_float2(p.normB[j], p.pot_in[j]) : make_float2(0.f, -CUDART_INF_F);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
@@ -259,6 +273,21 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float dot[32];
         tmem_ld32(taddr + (uint32_t)c0, dot);
+        if (MODE == 2) {
+          if (row < p.nA) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const int64_t j = j0 + c0 + c;
+              if (j < p.nB) {      // nB, n1 are multiples of 4 (checked on the host)
+                const float4 v = make_float4(dot[c] + ci[c0 + c].y, dot[c + 1] + ci[c0 + c + 1].y,
+                                             dot[c + 2] + ci[c0 + c + 2].y, dot[c + 3] + ci[c0 + c + 3].y);
+                float* dst = (j < p.n1) ? p.out1 + row * p.ld1 + j : p.out2 + row * p.ld2 + (j - p.n1);
+                *reinterpret_cast<float4*>(dst) = v;
+              }
+            }
+          }
+          continue;
+        }
         float z[32];
         float zmax = -CUDART_INF_F;
 #pragma unroll
@@ -311,7 +340,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         p.part_m[(int64_t)blockIdx.y * p.nA + row] = run_m;
         p.part_s[(int64_t)blockIdx.y * p.nA + row] = run_s;
       }
-    } else {
+    } else if (MODE == 1) {
       if (row < p.nA && p.row_sum) atomicAdd(&p.row_sum[row], run_s);
       loss_acc = warp_sum(loss_acc);
       if (lane == 0 && p.loss) atomicAdd(p.loss, loss_acc);
@@ -410,7 +439,7 @@ size_t lse_fused_tc_workspace(int64_t nA, int64_t nB, int d) {
 
 namespace tc {
 struct Launch {
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, ma2_hi, ma2_lo;
   Params p;
   int splits;
 };
@@ -427,6 +456,8 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
   if ((rc = make_map(&L->ma_lo, A_lo, nA, d_pad, BM))) return rc;
   if ((rc = make_map(&L->mb_hi, B_hi, nB, d_pad, BN))) return rc;
   if ((rc = make_map(&L->mb_lo, B_lo, nB, d_pad, BN))) return rc;
+  L->ma2_hi = L->ma_hi;
+  L->ma2_lo = L->ma_lo;
   Params& p = L->p;
   p = Params{};
   p.nA = nA; p.nB = nB; p.k_blocks = (d_pad + BK - 1) / BK; p.d_pad = d_pad; p.cost = cost; p.inv_reg = inv_reg;
@@ -436,6 +467,7 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
   if (!attr_set) {
     EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   return EG_OK;
@@ -455,7 +487,7 @@ int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, co
   L.p.part_m = reinterpret_cast<float*>(ws);
   L.p.part_s = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + half);
   dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);
-  lse_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.p);
+  lse_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
   EG_LAUNCHED();
   lse_combine_tc_kernel<<<(unsigned)ceil_div(nA, 256), 256, 0, s>>>(L.p.part_m, L.p.part_s, L.splits, nA, logw,
                                                                     pot_out, lse_out);
@@ -473,7 +505,48 @@ int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, c
   if (rc) return rc;
   L.p.pot_a = f; L.p.loss = loss; L.p.row_sum = row_sum;
   dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);
-  lse_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.p);
+  lse_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
+  EG_LAUNCHED();
+  return EG_OK;
+}
+
+
+// C[m, n] = [A1 | A2][m, k1+k2] · B[n, k1+k2]ᵀ + bias, fp32 in/out, 3xTF32 on tcgen05.  Operands are the hi/lo
+// splits (eg_split_tf32) with every K extent padded to a multiple of 16 (= one k-block).
+int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_hi, const float* A2_lo, int k2p,
+               int64_t m, const float* B_hi, const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1,
+               int64_t n1, float* out2, int64_t ld2, cudaStream_t s) {
+  using namespace tc;
+  if (k1p <= 0 || k1p % BK || k2p < 0 || k2p % BK || n % 4 || n1 % 4 || n1 > n || n1 <= 0) return EG_ERR_INVALID;
+  if (n1 < n && !out2) return EG_ERR_INVALID;
+  if (m >= (1ll << 31) || n >= (1ll << 31)) return EG_ERR_UNSUPPORTED;
+  if (((uintptr_t)out1 | (uintptr_t)out2) & 15 || (ld1 % 4) || (out2 && ld2 % 4)) return EG_ERR_INVALID;
+  Launch L;
+  int rc;
+  const int kp = k1p + k2p;
+  if ((rc = make_map(&L.ma_hi, A1_hi, m, k1p, BM))) return rc;
+  if ((rc = make_map(&L.ma_lo, A1_lo, m, k1p, BM))) return rc;
+  if (k2p) {
+    if ((rc = make_map(&L.ma2_hi, A2_hi, m, k2p, BM))) return rc;
+    if ((rc = make_map(&L.ma2_lo, A2_lo, m, k2p, BM))) return rc;
+  } else {
+    L.ma2_hi = L.ma_hi;
+    L.ma2_lo = L.ma_lo;
+  }
+  if ((rc = make_map(&L.mb_hi, B_hi, n, kp, BN))) return rc;
+  if ((rc = make_map(&L.mb_lo, B_lo, n, kp, BN))) return rc;
+  Params& p = L.p;
+  p = Params{};
+  p.nA = m; p.nB = n; p.k_blocks = kp / BK; p.d_pad = kp; p.kb_split = k1p / BK;
+  p.pot_in = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
+  p.tiles_per_split = (int)ceil_div(n, BN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(m, BM), 1);
+  lse_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
   EG_LAUNCHED();
   return EG_OK;
 }

@@ -86,6 +86,62 @@ class _Aggregate(torch.autograd.Function):
         return dH, d_gate, d_xres, None, None
 
 
+USE_TCGEN05_GEMM = True   # dense layer products on the 3xTF32 tcgen05 tiles; False -> everything on cuBLAS fp32
+
+
+class _DenseProducts(torch.autograd.Function):
+    """hidden = x·Wᵀ + b  and (highway) gate_pre = x·G + c  (layers/layers.py:61,69).
+
+    3xTF32 on tcgen05 is accurate to ~2e-6 relative, cuBLAS fp32 to ~2e-7.  That is irrelevant for
+    the smooth consumers (sigmoid gate, identity activation, the linear input gradient) but not
+    for a product that feeds a ReLU: an error of 2e-6 flips the sign of a handful of near-zero
+    pre-activations out of ~10^7, and each flip moves gradient entries by ~1e-3 relative — outside
+    the 1e-4 parity bar.  So `hidden` stays on cuBLAS fp32 when the layer's activation is ReLU
+    (`exact_hidden`), and goes through the tensor-core kernel otherwise; `gate_pre` and
+    dx = [dH | d_gate]·[Wᵀ | G]ᵀ always do.  dW = dHᵀ·x and db stay on cuBLAS / a reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gate_w, gate_b, exact_hidden):
+        n_out = weight.shape[0]
+        gate_pre = None
+        if exact_hidden:
+            hidden = F.linear(x, weight, bias)
+            if gate_w is not None:
+                gate_pre = ops.gemm_nt([x], gate_w.t().contiguous(), gate_b)
+        elif gate_w is None:
+            hidden = ops.gemm_nt([x], weight, bias)
+        else:
+            b0 = bias if bias is not None else torch.zeros(n_out, device=x.device)
+            hidden, gate_pre = ops.gemm_nt([x], torch.cat([weight, gate_w.t()], 0), torch.cat([b0, gate_b]), n1=n_out)
+        ctx.save_for_backward(x, weight, gate_w if gate_w is not None else weight.new_empty(0))
+        ctx.has_gate = gate_w is not None
+        ctx.has_bias = bias is not None
+        return hidden, gate_pre
+
+    @staticmethod
+    def backward(ctx, d_hidden, d_gate):
+        x, weight, gate_w = ctx.saved_tensors
+        dx = dW = db = None
+        if d_hidden is None:
+            d_hidden = torch.zeros(x.shape[0], weight.shape[0], device=x.device)
+        if ctx.needs_input_grad[0]:
+            if ctx.has_gate and d_gate is not None:
+                dx = ops.gemm_nt([d_hidden, d_gate], torch.cat([weight.t(), gate_w], 1))
+            else:
+                dx = ops.gemm_nt([d_hidden], weight.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            dW = d_hidden.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = d_hidden.sum(0)
+        return dx, dW, db, None, None, None
+
+
+def _tc_gemm_ok(x, linear, gate_w=None):
+    return (USE_TCGEN05_GEMM and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+            and linear.out_features % 4 == 0 and x.shape[0] > 0
+            and (gate_w is None or gate_w.shape[1] % 4 == 0))
+
+
 def _dense(x):
     # the reference stores the (fully dense) feature matrix as sparse COO (utils/data_utils.py:358,397)
     return x.to_dense() if x.is_sparse else x
@@ -124,7 +180,11 @@ class GraphConvolution(Module):
     def forward(self, input):
         x, adj = input
         x = _dense(x)
-        hidden = self.linear.forward(x)
+        if _tc_gemm_ok(x, self.linear):
+            hidden, _ = _DenseProducts.apply(x, self.linear.weight, self.linear.bias, None, None,
+                                             self._act_code != _lib.ACT_IDENTITY)
+        else:
+            hidden = self.linear.forward(x)
         hidden = F.dropout(hidden, self.dropout, training=self.training)
         return self._aggregate(hidden, adj), adj
 
@@ -153,12 +213,16 @@ class HighWayGraphConvolution(GraphConvolution):
     def forward(self, input):
         x, adj = input
         x = _dense(x)
-        hidden = self.linear.forward(x)
-        hidden = F.dropout(hidden, self.dropout, training=self.training)
         if self.kernel_gate.device != x.device:      # reference moves them in __init__ only
             self.kernel_gate = self.kernel_gate.to(x.device)
             self.bias_gate = self.bias_gate.to(x.device)
-        gate_pre = torch.addmm(self.bias_gate, x, self.kernel_gate)
+        if _tc_gemm_ok(x, self.linear, self.kernel_gate):
+            hidden, gate_pre = _DenseProducts.apply(x, self.linear.weight, self.linear.bias, self.kernel_gate,
+                                                    self.bias_gate, self._act_code != _lib.ACT_IDENTITY)
+        else:
+            hidden = self.linear.forward(x)
+            gate_pre = torch.addmm(self.bias_gate, x, self.kernel_gate)
+        hidden = F.dropout(hidden, self.dropout, training=self.training)
         return self._aggregate(hidden, adj, gate_pre, x), adj
 
 

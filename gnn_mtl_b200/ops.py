@@ -291,3 +291,48 @@ def plan_fused(A, B, cost, inv_reg, f, g, want_plan=False, want_rows=True, algo=
                                 float(inv_reg), ptr(f), ptr(g), ptr(P), B.n, ptr(loss), ptr(rs),
                                 ptr(A.hi), ptr(A.lo), ptr(B.hi), ptr(B.lo), stream()), "eg_plan_fused")
     return P, loss[0], rs
+
+
+# ---- dense layer products on the tcgen05 3xTF32 tiles -----------------------------------------
+
+def _pad16(k):
+    return (k + 15) // 16 * 16
+
+
+def gemm_nt(A_parts, B, bias=None, n1=None):
+    """C = [A1 | A2 ...] · Bᵀ + bias with fp32 accuracy (3xTF32 on tcgen05).
+    A_parts: one or two [m, k_i] fp32 CUDA tensors; B: [n, sum k_i] fp32 (row j = output column j).
+    Returns out1 [m, n1] (and out2 [m, n - n1] when n1 < n)."""
+    A_parts = [_f32c(a) for a in A_parts]
+    if not 1 <= len(A_parts) <= 2:
+        raise ValueError("gemm_nt takes one or two A operands")
+    m = A_parts[0].shape[0]
+    ks = [a.shape[1] for a in A_parts]
+    B = _f32c(B)
+    n = B.shape[0]
+    if B.shape[1] != sum(ks):
+        raise ValueError("gemm_nt: B has %d columns, A parts have %s" % (B.shape[1], ks))
+    n1 = n if n1 is None else n1
+    dev = B.device
+    splits = [split_tf32(a, _pad16(a.shape[1])) for a in A_parts]
+    # B's K axis is laid out part by part, each padded to 16, to match the k-blocks of the A parts
+    if len(ks) == 1 and ks[0] % 16 == 0:
+        Bp = B
+    else:
+        Bp = torch.zeros(n, sum(_pad16(k) for k in ks), dtype=torch.float32, device=dev)
+        src = dst = 0
+        for k in ks:
+            Bp[:, dst:dst + k] = B[:, src:src + k]
+            src += k
+            dst += _pad16(k)
+    b_hi, b_lo = split_tf32(Bp, Bp.shape[1])
+    out1 = torch.empty(m, n1, dtype=torch.float32, device=dev)
+    out2 = torch.empty(m, n - n1, dtype=torch.float32, device=dev) if n1 < n else None
+    a2_hi, a2_lo = (splits[1] if len(splits) == 2 else (None, None))
+    bias = _f32c(bias) if bias is not None else None
+    with torch.cuda.device(dev):
+        check(lib.eg_gemm_nt_3xtf32(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
+                                    _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
+                                    ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
+              "eg_gemm_nt_3xtf32")
+    return (out1, out2) if out2 is not None else out1

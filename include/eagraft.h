@@ -189,6 +189,18 @@ int eg_plan_fused(int algo, int cost, const float* A, int64_t nA, const float* B
                   const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
                   eg_stream_t stream);
 
+/* ---- dense products of the layers on the same tcgen05 3xTF32 tiles ----------------
+ * C[m, n] = [A1 | A2][m, k1+k2] · B[n, k1+k2]ᵀ + bias[n]   (fp32 accuracy, fp32 in/out)
+ * Serves  x·Wᵀ + b  and  x·G + c  of layers/layers.py:61,69 in one launch
+ * (B = [W ; Gᵀ], columns [0,n1) -> out1 = hidden, [n1,n) -> out2 = gate_pre) and their
+ * input gradient  dx = [dH | d_gate] · [Wᵀ | G]ᵀ.  All operands are eg_split_tf32
+ * outputs whose K extents (k1_pad, k2_pad, and B's k1_pad+k2_pad) are multiples of 16;
+ * A2 may be NULL with k2_pad = 0; out2 may be NULL when n1 == n; n, n1, ld1, ld2 % 4 == 0. */
+int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
+                      const float* A2_hi, const float* A2_lo, int k2_pad, int64_t m,
+                      const float* B_hi, const float* B_lo, int64_t n, const float* bias,
+                      float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -371,3 +371,23 @@ def test_abi_error_behaviour(dev):
     with pytest.raises(_lib.EagraftError):
         from gnn_mtl_b200 import ops
         ops.l1_matrix(torch.zeros(2, 2), torch.zeros(2, 2))               # CPU tensors are refused
+
+
+@pytest.mark.parametrize("m,k,n,n1", [(1, 4, 4, 4), (130, 300, 600, 300), (777, 52, 260, 128), (3000, 300, 300, 300)])
+def test_gemm_nt_3xtf32_matches_fp64(m, k, n, n1, dev):
+    """layers' dense products on tcgen05: fp32-accurate (3xTF32) against an fp64 reference."""
+    from gnn_mtl_b200 import ops
+    torch.manual_seed(m)
+    A = torch.randn(m, k, device=dev)
+    B = torch.randn(n, k, device=dev) * 0.1
+    bias = torch.randn(n, device=dev)
+    res = ops.gemm_nt([A], B, bias, n1=n1)
+    got = torch.cat(res, 1) if isinstance(res, tuple) else res
+    ref = A.double() @ B.double().t() + bias.double()
+    assert relerr(got, ref) < 1e-5      # 3xTF32: ~2e-6 at k = 300
+    # K-concatenated operand: [A1 | A2] · Bᵀ
+    A2 = torch.randn(m, 36, device=dev)
+    B2 = torch.randn(n, k + 36, device=dev) * 0.1
+    got2 = ops.gemm_nt([A, A2], B2)
+    ref2 = torch.cat([A, A2], 1).double() @ B2.double().t()
+    assert relerr(got2, ref2) < 1e-5
