@@ -546,6 +546,235 @@ sinkhorn_persistent_kernel(const T* __restrict__ M, int64_t I, int64_t J, int64_
   if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = final_buf; st->err = err; }
 }
 
+
+// ---- fully on-chip variant for the reference's batch size (3000 x 3000 fp32, `config.py:30`) -----------
+// Same sweep structure as sinkhorn_persistent_kernel, but the CTA's whole row block stays on the SM:
+// S rows in shared memory + up to kOcRR rows in registers (thread t keeps its own 16-byte column groups of
+// those rows), so phases C and U never wait on L2.  512 threads (128 registers each), 2 column groups per
+// thread => J <= 4096.
+constexpr int kOcThreads = 512;
+constexpr int kOcWarps = kOcThreads / 32;
+constexpr int kOcQ = 2;     // column groups (float4) per thread
+constexpr int kOcRR = 5;    // rows kept in registers
+
+__global__ void __launch_bounds__(kOcThreads, 1)
+sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld, float inv_reg,
+                       const float* __restrict__ log_a, const float* __restrict__ log_b, const float* __restrict__ b,
+                       int max_iter, double stop_thr, float* __restrict__ part_m, float* __restrict__ part_s,
+                       float* __restrict__ lv_buf, float* __restrict__ log_u_out, float* __restrict__ log_v_out,
+                       PersistState* __restrict__ st, int S_max) {
+  using T = float;
+  extern __shared__ __align__(16) unsigned char smem_raw_o[];
+  const int nb = gridDim.x, cta = blockIdx.x;
+  const int rows_per = (int)((I + nb - 1) / nb);
+  const int64_t row0 = min(I, (int64_t)cta * rows_per);
+  const int R = (int)(min(I, row0 + rows_per) - row0);
+  const int S = min(R, S_max);                              // rows [0,S) in smem, [S,R) in registers (R-S <= kOcRR)
+  const int cols_per = (J + nb - 1) / nb;
+  const int col0 = min(J, cta * cols_per), col1 = min(J, col0 + cols_per);
+  const int ng = J / 4;
+  float* lv_s = reinterpret_cast<float*>(smem_raw_o);      // [J]
+  float* lu_s = lv_s + J;                                   // [32]
+  float* red_m = lu_s + 32;                                 // [kOcWarps][32]
+  float* red_s = red_m + kOcWarps * 32;
+  float* rr_m = red_s + kOcWarps * 32;                      // [kOcWarps][kOcRR]
+  float* rr_s = rr_m + kOcWarps * 8;
+  float4* m_res = reinterpret_cast<float4*>(rr_s + kOcWarps * 8);   // [S][ng]
+  __shared__ double err_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned int target = 0;
+
+  int gq[kOcQ];
+  bool gok[kOcQ];
+#pragma unroll
+  for (int q = 0; q < kOcQ; ++q) { gq[q] = tid + kOcThreads * q; gok[q] = gq[q] < ng; }
+  float4 mreg[kOcRR][kOcQ];
+#pragma unroll
+  for (int rr = 0; rr < kOcRR; ++rr)
+#pragma unroll
+    for (int q = 0; q < kOcQ; ++q) {
+      const bool live = gok[q] && (S + rr < R);
+      mreg[rr][q] = live ? reinterpret_cast<const float4*>(M + (row0 + S + rr) * ld)[gq[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  for (int r = 0; r < S; ++r) {
+    const float4* src = reinterpret_cast<const float4*>(M + (row0 + r) * ld);
+    for (int g = tid; g < ng; g += kOcThreads) m_res[r * ng + g] = src[g];
+  }
+  for (int r = tid; r < 32; r += kOcThreads) lu_s[r] = (r < R) ? (float)(-log((double)I)) : -CUDART_INF_F;
+  __syncthreads();
+
+  int cpt = 0, sweeps = 0, final_buf = 0;
+  double err = 1.0;
+  bool stopped = false;
+  const bool timer = (cta == 0 && tid == 0);
+  for (cpt = 0; cpt < max_iter; ++cpt) {
+    const int cur = cpt & 1, nxt = cur ^ 1;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    if (timer) t0 = gtime();
+    // ---- C: partial column LSE over my rows ---------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < kOcQ; ++q) {
+      if (!gok[q]) continue;
+      Lse<T> acc[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[v].init();
+      const float4* sbase = m_res + gq[q];
+      for (int r0 = 0; r0 < S; r0 += 4) {
+        float z[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          const float4 mv = (r < S) ? sbase[r * ng] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float lu = (r < S) ? lu_s[r] : -CUDART_INF_F;
+          z[u][0] = fmaf(-mv.x, inv_reg, lu); z[u][1] = fmaf(-mv.y, inv_reg, lu);
+          z[u][2] = fmaf(-mv.z, inv_reg, lu); z[u][3] = fmaf(-mv.w, inv_reg, lu);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[v].push4(z[0][v], z[1][v], z[2][v], z[3][v]);
+      }
+      {
+        float z[kOcRR][4];
+#pragma unroll
+        for (int rr = 0; rr < kOcRR; ++rr) {
+          const float lu = lu_s[S + rr];                    // -inf beyond R (lu_s is padded to 32 entries)
+          z[rr][0] = fmaf(-mreg[rr][q].x, inv_reg, lu); z[rr][1] = fmaf(-mreg[rr][q].y, inv_reg, lu);
+          z[rr][2] = fmaf(-mreg[rr][q].z, inv_reg, lu); z[rr][3] = fmaf(-mreg[rr][q].w, inv_reg, lu);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          acc[v].push4(z[0][v], z[1][v], z[2][v], z[3][v]);
+          acc[v].push1(z[4][v]);
+        }
+      }
+      float4 pm = make_float4(acc[0].m, acc[1].m, acc[2].m, acc[3].m);
+      float4 ps = make_float4(acc[0].s, acc[1].s, acc[2].s, acc[3].s);
+      reinterpret_cast<float4*>(part_m + (int64_t)cta * J)[gq[q]] = pm;
+      reinterpret_cast<float4*>(part_s + (int64_t)cta * J)[gq[q]] = ps;
+    }
+    if (timer) t1 = gtime();
+    grid_barrier(&st->barrier, target, nb);
+    if (timer) t2 = gtime();
+    // ---- R: merge all CTAs' partials for my slice of columns -> log v ---------------------------------
+    const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
+    const int slot = check ? ((cpt - 1) / 10) & 127 : 0;
+    if (tid == 0) err_s = 0.0;
+    for (int c0 = col0; c0 < col1; c0 += 32) {
+      const int j = c0 + lane;
+      Lse<T> acc;
+      acc.init();
+      if (j < col1) {
+        float pm[10], ps[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const int pidx = warp + kOcWarps * k;
+          pm[k] = (pidx < nb) ? __ldcg(part_m + (int64_t)pidx * J + j) : -CUDART_INF_F;
+          ps[k] = (pidx < nb) ? __ldcg(part_s + (int64_t)pidx * J + j) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc.merge(pm[k], ps[k]);
+      }
+      red_m[warp * 32 + lane] = acc.m;
+      red_s[warp * 32 + lane] = acc.s;
+      __syncthreads();
+      {
+        // warp w (and w + 16) finishes column c0 + w: lanes 0..15 hold the per-warp partials
+        for (int cw = warp; cw < 32; cw += kOcWarps) {
+          const int jc = c0 + cw;
+          Lse<T> tot;
+          tot.m = (lane < kOcWarps) ? red_m[lane * 32 + cw] : -CUDART_INF_F;
+          tot.s = (lane < kOcWarps) ? red_s[lane * 32 + cw] : 0.f;
+          warp_merge(tot);
+          if (lane == 0 && jc < col1) {
+            const float lse = tot.value();
+            if (check) {
+              const double d = (double)__expf(__ldcg(lv_buf + (int64_t)cur * J + jc) + lse) - (double)b[jc];
+              atomicAdd(&err_s, d * d);
+            }
+            lv_buf[(int64_t)nxt * J + jc] = log_b[jc] - lse;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (check && tid == 0 && err_s != 0.0) atomicAdd(&st->err2[slot], err_s);
+    if (timer) t3 = gtime();
+    grid_barrier(&st->barrier, target, nb);
+    if (timer) t4 = gtime();
+    if (check) {
+      double e2;
+      asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(e2) : "l"(&st->err2[slot]) : "memory");
+      err = sqrt(e2);
+      if (!(err > stop_thr)) { stopped = true; final_buf = cur; break; }
+    }
+    // ---- U: row update for my rows with the new log v ---------------------------------------------------
+    {
+      const float4* src = reinterpret_cast<const float4*>(lv_buf + (int64_t)nxt * J);
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (gok[0]) v0 = __ldcg(src + gq[0]);
+      if (gok[1]) v1 = __ldcg(src + gq[1]);
+      if (gok[0]) reinterpret_cast<float4*>(lv_s)[gq[0]] = v0;
+      if (gok[1]) reinterpret_cast<float4*>(lv_s)[gq[1]] = v1;
+      // register rows: this thread's columns of rows S..R-1 (it already holds the matching log v values)
+      Lse<T> racc[kOcRR];
+#pragma unroll
+      for (int rr = 0; rr < kOcRR; ++rr) {
+        racc[rr].init();
+        if (gok[0])
+          racc[rr].push4(fmaf(-mreg[rr][0].x, inv_reg, v0.x), fmaf(-mreg[rr][0].y, inv_reg, v0.y),
+                         fmaf(-mreg[rr][0].z, inv_reg, v0.z), fmaf(-mreg[rr][0].w, inv_reg, v0.w));
+        if (gok[1])
+          racc[rr].push4(fmaf(-mreg[rr][1].x, inv_reg, v1.x), fmaf(-mreg[rr][1].y, inv_reg, v1.y),
+                         fmaf(-mreg[rr][1].z, inv_reg, v1.z), fmaf(-mreg[rr][1].w, inv_reg, v1.w));
+        warp_merge(racc[rr]);
+        if (lane == 0) { rr_m[warp * 8 + rr] = racc[rr].m; rr_s[warp * 8 + rr] = racc[rr].s; }
+      }
+    }
+    __syncthreads();
+    {
+      const float4* pv = reinterpret_cast<const float4*>(lv_s);
+      for (int r = warp; r < S; r += kOcWarps) {
+        const float4* mrow = m_res + r * ng;
+        Lse<T> acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u].init();
+        for (int g0 = lane; g0 < ng; g0 += 32 * 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int g = g0 + 32 * u;
+            if (g < ng) {
+              const float4 e = mrow[g], l = pv[g];
+              acc[u].push4(fmaf(-e.x, inv_reg, l.x), fmaf(-e.y, inv_reg, l.y), fmaf(-e.z, inv_reg, l.z),
+                           fmaf(-e.w, inv_reg, l.w));
+            }
+          }
+        }
+        acc[0].merge(acc[1].m, acc[1].s);
+        acc[2].merge(acc[3].m, acc[3].s);
+        acc[0].merge(acc[2].m, acc[2].s);
+        warp_merge(acc[0]);
+        if (lane == 0) lu_s[r] = log_a[row0 + r] - acc[0].value();
+      }
+      if (warp == 0 && lane < kOcRR && S + lane < R) {       // finish the register rows: 16 per-warp partials each
+        Lse<T> tot;
+        tot.init();
+#pragma unroll
+        for (int w = 0; w < kOcWarps; ++w) tot.merge(rr_m[w * 8 + lane], rr_s[w * 8 + lane]);
+        lu_s[S + lane] = log_a[row0 + S + lane] - tot.value();
+      }
+    }
+    __syncthreads();
+    sweeps = cpt + 1;
+    if (timer) {
+      st->t_phase[0] += t1 - t0; st->t_phase[1] += t2 - t1; st->t_phase[2] += t3 - t2;
+      st->t_phase[3] += t4 - t3; st->t_phase[4] += gtime() - t4;
+    }
+  }
+  if (!stopped) final_buf = max_iter & 1;
+  for (int r = tid; r < R; r += kOcThreads) log_u_out[row0 + r] = lu_s[r];
+  for (int j = col0 + tid; j < col1; j += kOcThreads) log_v_out[j] = __ldcg(lv_buf + (int64_t)final_buf * J + j);
+  if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = final_buf; st->err = err; }
+}
+
 template <typename T>
 struct SolveWs {
   T *log_a, *log_b, *lv_alt, *col_lse;
@@ -575,6 +804,7 @@ static SolveWs<T> carve_solve(void* ws, int64_t I, int64_t J) {
 
 int g_tune_persistent = 1;   // eg_debug_set(3, 0) forces the streaming path
 int g_tune_resident = 1;     // eg_debug_set(4, 0) keeps no rows of M in shared memory
+int g_tune_onchip = 1;       // eg_debug_set(5, 0) disables the fully on-chip fp32 kernel
 
 // One cooperative launch for the whole solve when the shape allows it.
 template <typename T>
@@ -590,10 +820,56 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
   EG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (!coop || sms > kNumSMs) return EG_OK;
   const int64_t rows_per = ceil_div(I, (int64_t)sms);
-  const size_t fixed = sizeof(T) * (size_t)(J + (rows_per + 3) / 4 * 4 + 2 * 32 * (kPersistThreads / 32)) + 16;
-  if (fixed > 160 * 1024) return EG_OK;
   int max_smem = 0;
   EG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if constexpr (sizeof(T) == 4) {
+    // whole row block on chip (shared memory + registers)?  Needs J <= 4096 and rows_per <= S + kOcRR, nb <= 160.
+    const size_t oc_fixed = sizeof(float) * (size_t)(J + 32 + 2 * 32 * kOcWarps + 2 * 8 * kOcWarps) + 16;
+    const int64_t s_fit = ((int64_t)max_smem - 1024 - (int64_t)oc_fixed) / (int64_t)(sizeof(float) * (size_t)J);
+    const int64_t s_need = std::max<int64_t>(rows_per - kOcRR, std::min<int64_t>(rows_per, kOcWarps));
+    if (g_tune_onchip && J <= 4 * kOcThreads * kOcQ && rows_per <= 32 && sms <= 160 && s_need <= s_fit &&
+        rows_per - s_need <= kOcRR && rows_per - s_need >= 0) {
+      int S_max = (int)s_need;
+      const size_t smem = oc_fixed + sizeof(float) * (size_t)J * (size_t)S_max;
+      auto kern = sinkhorn_onchip_kernel;
+      EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      EG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kOcThreads, smem));
+      if (per_sm >= 1) {
+        const int TB = 256;
+        log_kernel<T><<<(unsigned)ceil_div(I, TB), TB, 0, s>>>(a, I, w.log_a); EG_LAUNCHED();
+        log_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(b, J, w.log_b); EG_LAUNCHED();
+        fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log((double)J))); EG_LAUNCHED();
+        EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
+        float inv_reg = (float)(1.0 / reg);
+        int64_t ld = J;
+        int Ji = (int)J;
+        void* args[] = {(void*)&M, (void*)&I, (void*)&Ji, (void*)&ld, (void*)&inv_reg, (void*)&w.log_a,
+                        (void*)&w.log_b, (void*)&b, (void*)&max_iter, (void*)&stop_thr, (void*)&w.part_m,
+                        (void*)&w.part_s, (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&w.state,
+                        (void*)&S_max};
+        EG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)sms), dim3(kOcThreads), args, smem, s));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        PersistState host_state;
+        EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(int) * 3 + sizeof(double) + 4, cudaMemcpyDeviceToHost, s));
+        EG_CUDA(cudaStreamSynchronize(s));
+        if (h_sweeps) *h_sweeps = host_state.sweeps;
+        if (h_err) *h_err = host_state.err;
+        if (getenv("EG_PERSIST_TIMING")) {
+          PersistState full;
+          cudaMemcpy(&full, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost);
+          fprintf(stderr, "[eagraft] on-chip sinkhorn (S=%d): %d sweeps; CTA0 us/sweep: C %.2f | bar %.2f | R %.2f | bar %.2f | U %.2f\n",
+                  S_max, full.sweeps, full.t_phase[0] / 1e3 / full.sweeps, full.t_phase[1] / 1e3 / full.sweeps,
+                  full.t_phase[2] / 1e3 / full.sweeps, full.t_phase[3] / 1e3 / full.sweeps,
+                  full.t_phase[4] / 1e3 / full.sweeps);
+        }
+        *used = true;
+        return EG_OK;
+      }
+    }
+  }
+  const size_t fixed = sizeof(T) * (size_t)(J + (rows_per + 3) / 4 * 4 + 2 * 32 * (kPersistThreads / 32)) + 16;
+  if (fixed > 160 * 1024) return EG_OK;
   // as many rows of the CTA's block as fit stay resident in shared memory for the whole solve
   int rows_resident = (int)std::min<int64_t>(rows_per, ((int64_t)max_smem - 1024 - (int64_t)fixed) /
                                                          (int64_t)(sizeof(T) * (size_t)J));

@@ -20,6 +20,7 @@ int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 e
 int g_tune_warps = 4;       // warps (= rows) per CTA
 extern int g_tune_persistent;
 extern int g_tune_resident;
+extern int g_tune_onchip;
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
 
 struct Epilogue {
@@ -302,6 +303,7 @@ int eg_debug_set(int key, int value) {
   else if (key == 2) eg::g_tune_hints = value;
   else if (key == 3) eg::g_tune_persistent = value;
   else if (key == 4) eg::g_tune_resident = value;
+  else if (key == 5) eg::g_tune_onchip = value;
   else return EG_ERR_INVALID;
   return EG_OK;
 }
