@@ -213,6 +213,10 @@ def plan_dense(M, inv_reg, f, g, want_plan=True, want_rows=False, want_cols=Fals
     return P, loss[0], rs, cs
 
 
+# bench.py sets this to a list to collect (start_event, end_event, I, J, sweeps, itemsize) per solve
+SINKHORN_TIMER = None
+
+
 def sinkhorn_dense(M, a, b, reg, max_iter, stop_thr):
     """Device solver of utils/ot_loss.py:26-76; returns (log_u, log_v, sweeps, err)."""
     dt = _dt(M)
@@ -225,9 +229,15 @@ def sinkhorn_dense(M, a, b, reg, max_iter, stop_thr):
         ws_bytes = int(lib.eg_sinkhorn_dense_workspace_bytes(dt, I, J))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         sweeps, err = C.c_int(0), C.c_double(0.0)
+        if SINKHORN_TIMER is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(lib.eg_sinkhorn_dense(dt, ptr(M), I, J, float(reg), ptr(a), ptr(b), int(max_iter), float(stop_thr),
                                     ptr(Mt), ptr(log_u), ptr(log_v), ptr(ws), ws_bytes, C.byref(sweeps),
                                     C.byref(err), stream()), "eg_sinkhorn_dense")
+        if SINKHORN_TIMER is not None:
+            ev1.record()
+            SINKHORN_TIMER.append((ev0, ev1, I, J, int(sweeps.value), M.element_size()))
     return log_u, log_v, int(sweeps.value), float(err.value)
 
 

@@ -187,8 +187,8 @@ def sinkhorn_scaling(a, b, M, reg, numItermax=1000, stopThr=1e-9, return_info=Fa
     M = M.detach().to(torch.float64)
     n_src, n_tgt = M.shape
     assert a.numel() == n_src and b.numel() == n_tgt
-    u = torch.full((n_src, 1), 1.0 / n_src, dtype=torch.float64)
-    v = torch.full((n_tgt, 1), 1.0 / n_tgt, dtype=torch.float64)
+    u = torch.full((n_src, 1), 1.0 / n_src, dtype=torch.float64, device=M.device)
+    v = torch.full((n_tgt, 1), 1.0 / n_tgt, dtype=torch.float64, device=M.device)
     K = torch.exp(M / (-reg))
     K_over_a = K / a.reshape(-1, 1)
     sweeps, err, failed = 0, 1.0, False
@@ -290,10 +290,10 @@ def wasserstein_loss_as_shipped(X, Y, reg=0.01, numItermax=1000, stopThr=1e-9):
     """
     n = X.shape[0]
     M = torch.cdist(X, Y, p=2)
-    sinkhorn_scaling(torch.ones(n), torch.ones(Y.shape[0]), M.detach(), reg,
+    sinkhorn_scaling(torch.ones(n, device=X.device), torch.ones(Y.shape[0], device=X.device), M.detach(), reg,
                      numItermax=numItermax, stopThr=stopThr)
     pick = torch.zeros_like(M)
-    pick[torch.arange(n), torch.zeros(n, dtype=torch.long)] = 1
+    pick[torch.arange(n, device=X.device), torch.zeros(n, dtype=torch.long, device=X.device)] = 1
     return (pick * M).sum()
 
 
