@@ -61,14 +61,19 @@ struct Lse {
   __device__ __forceinline__ T value() const { return (s > T(0)) ? m + Num<T>::log_(s) : Num<T>::ninf(); }
 };
 
+// Warp all-reduce of (max, sum) pairs: max first (no transcendental), ONE rescale per lane, then a plain
+// sum — 1 exp per lane instead of 2 per shuffle level.
 template <typename T>
 __device__ __forceinline__ void warp_merge(Lse<T>& a) {
+  T mx = a.m;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    T om = __shfl_xor_sync(0xffffffffu, a.m, o);
-    T os = __shfl_xor_sync(0xffffffffu, a.s, o);
-    a.merge(om, os);
-  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const T ref = (mx == Num<T>::ninf()) ? T(0) : mx;
+  T sum = a.s * Num<T>::exp_(a.m - ref);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  a.m = mx;
+  a.s = sum;
 }
 
 // One CTA of kRowThreads per row when rows are long, one warp per row otherwise.
@@ -557,6 +562,43 @@ constexpr int kOcWarps = kOcThreads / 32;
 constexpr int kOcQ = 2;     // column groups (float4) per thread
 constexpr int kOcRR = 5;    // rows kept in registers
 
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// (max, sum) pair in log2 units; merge = one ex2 per operand.
+struct Lse2 {
+  float m, s;
+  __device__ __forceinline__ void init() { m = -CUDART_INF_F; s = 0.f; }
+  __device__ __forceinline__ void merge(float om, float os) {
+    const float mx = fmaxf(m, om);
+    const float ref = (mx == -CUDART_INF_F) ? 0.f : mx;
+    s = s * ex2f(m - ref) + os * ex2f(om - ref);
+    m = mx;
+  }
+  __device__ __forceinline__ float value() const { return (s > 0.f) ? m + lg2f(s) : -CUDART_INF_F; }
+};
+__device__ __forceinline__ void warp_merge2(Lse2& a) {
+  float mx = a.m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float ref = (mx == -CUDART_INF_F) ? 0.f : mx;
+  float sum = a.s * ex2f(a.m - ref);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  a.m = mx;
+  a.s = sum;
+}
+
 __global__ void __launch_bounds__(kOcThreads, 1)
 sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld, float inv_reg,
                        const float* __restrict__ log_a, const float* __restrict__ log_b, const float* __restrict__ b,
@@ -583,6 +625,7 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
   __shared__ double err_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned int target = 0;
+  const float inv2 = inv_reg * kLog2e;       // all potentials inside this kernel are in log2 units
 
   int gq[kOcQ];
   bool gok[kOcQ];
@@ -600,7 +643,7 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
     const float4* src = reinterpret_cast<const float4*>(M + (row0 + r) * ld);
     for (int g = tid; g < ng; g += kOcThreads) m_res[r * ng + g] = src[g];
   }
-  for (int r = tid; r < 32; r += kOcThreads) lu_s[r] = (r < R) ? (float)(-log((double)I)) : -CUDART_INF_F;
+  for (int r = tid; r < 32; r += kOcThreads) lu_s[r] = (r < R) ? (float)(-log2((double)I)) : -CUDART_INF_F;
   __syncthreads();
 
   int cpt = 0, sweeps = 0, final_buf = 0;
@@ -611,45 +654,44 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
     const int cur = cpt & 1, nxt = cur ^ 1;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
     if (timer) t0 = gtime();
-    // ---- C: partial column LSE over my rows ---------------------------------------------------------
+    // ---- C: partial column LSE over my rows (two passes over on-chip data: max, then one exp2 each) ----
+    // everything in log2 units: z2 = (log u_i - M_ij/reg) * log2(e)
 #pragma unroll
     for (int q = 0; q < kOcQ; ++q) {
       if (!gok[q]) continue;
-      Lse<T> acc[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) acc[v].init();
       const float4* sbase = m_res + gq[q];
-      for (int r0 = 0; r0 < S; r0 += 4) {
-        float z[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u;
-          const float4 mv = (r < S) ? sbase[r * ng] : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float lu = (r < S) ? lu_s[r] : -CUDART_INF_F;
-          z[u][0] = fmaf(-mv.x, inv_reg, lu); z[u][1] = fmaf(-mv.y, inv_reg, lu);
-          z[u][2] = fmaf(-mv.z, inv_reg, lu); z[u][3] = fmaf(-mv.w, inv_reg, lu);
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[v].push4(z[0][v], z[1][v], z[2][v], z[3][v]);
+      float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll 4
+      for (int r = 0; r < S; ++r) {
+        const float4 mv = sbase[r * ng];
+        const float lu = lu_s[r];
+        mx[0] = fmaxf(mx[0], fmaf(-mv.x, inv2, lu)); mx[1] = fmaxf(mx[1], fmaf(-mv.y, inv2, lu));
+        mx[2] = fmaxf(mx[2], fmaf(-mv.z, inv2, lu)); mx[3] = fmaxf(mx[3], fmaf(-mv.w, inv2, lu));
       }
-      {
-        float z[kOcRR][4];
 #pragma unroll
-        for (int rr = 0; rr < kOcRR; ++rr) {
-          const float lu = lu_s[S + rr];                    // -inf beyond R (lu_s is padded to 32 entries)
-          z[rr][0] = fmaf(-mreg[rr][q].x, inv_reg, lu); z[rr][1] = fmaf(-mreg[rr][q].y, inv_reg, lu);
-          z[rr][2] = fmaf(-mreg[rr][q].z, inv_reg, lu); z[rr][3] = fmaf(-mreg[rr][q].w, inv_reg, lu);
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          acc[v].push4(z[0][v], z[1][v], z[2][v], z[3][v]);
-          acc[v].push1(z[4][v]);
-        }
+      for (int rr = 0; rr < kOcRR; ++rr) {
+        const float lu = lu_s[S + rr];                      // -inf beyond R (lu_s is padded to 32 entries)
+        mx[0] = fmaxf(mx[0], fmaf(-mreg[rr][q].x, inv2, lu)); mx[1] = fmaxf(mx[1], fmaf(-mreg[rr][q].y, inv2, lu));
+        mx[2] = fmaxf(mx[2], fmaf(-mreg[rr][q].z, inv2, lu)); mx[3] = fmaxf(mx[3], fmaf(-mreg[rr][q].w, inv2, lu));
       }
-      float4 pm = make_float4(acc[0].m, acc[1].m, acc[2].m, acc[3].m);
-      float4 ps = make_float4(acc[0].s, acc[1].s, acc[2].s, acc[3].s);
-      reinterpret_cast<float4*>(part_m + (int64_t)cta * J)[gq[q]] = pm;
-      reinterpret_cast<float4*>(part_s + (int64_t)cta * J)[gq[q]] = ps;
+      float ref[4], sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int v = 0; v < 4; ++v) ref[v] = (mx[v] == -CUDART_INF_F) ? 0.f : mx[v];
+#pragma unroll 4
+      for (int r = 0; r < S; ++r) {
+        const float4 mv = sbase[r * ng];
+        const float lu = lu_s[r];
+        sum[0] += ex2f(fmaf(-mv.x, inv2, lu) - ref[0]); sum[1] += ex2f(fmaf(-mv.y, inv2, lu) - ref[1]);
+        sum[2] += ex2f(fmaf(-mv.z, inv2, lu) - ref[2]); sum[3] += ex2f(fmaf(-mv.w, inv2, lu) - ref[3]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < kOcRR; ++rr) {
+        const float lu = lu_s[S + rr];
+        sum[0] += ex2f(fmaf(-mreg[rr][q].x, inv2, lu) - ref[0]); sum[1] += ex2f(fmaf(-mreg[rr][q].y, inv2, lu) - ref[1]);
+        sum[2] += ex2f(fmaf(-mreg[rr][q].z, inv2, lu) - ref[2]); sum[3] += ex2f(fmaf(-mreg[rr][q].w, inv2, lu) - ref[3]);
+      }
+      reinterpret_cast<float4*>(part_m + (int64_t)cta * J)[gq[q]] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+      reinterpret_cast<float4*>(part_s + (int64_t)cta * J)[gq[q]] = make_float4(sum[0], sum[1], sum[2], sum[3]);
     }
     if (timer) t1 = gtime();
     grid_barrier(&st->barrier, target, nb);
@@ -660,7 +702,7 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
     if (tid == 0) err_s = 0.0;
     for (int c0 = col0; c0 < col1; c0 += 32) {
       const int j = c0 + lane;
-      Lse<T> acc;
+      Lse2 acc;
       acc.init();
       if (j < col1) {
         float pm[10], ps[10];
@@ -670,8 +712,16 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
           pm[k] = (pidx < nb) ? __ldcg(part_m + (int64_t)pidx * J + j) : -CUDART_INF_F;
           ps[k] = (pidx < nb) ? __ldcg(part_s + (int64_t)pidx * J + j) : 0.f;
         }
+        // max first, then one ex2 per partial (no dependent merge chain)
+        float mx = pm[0];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) acc.merge(pm[k], ps[k]);
+        for (int k = 1; k < 10; ++k) mx = fmaxf(mx, pm[k]);
+        const float ref = (mx == -CUDART_INF_F) ? 0.f : mx;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sum += ps[k] * ex2f(pm[k] - ref);
+        acc.m = mx;
+        acc.s = sum;
       }
       red_m[warp * 32 + lane] = acc.m;
       red_s[warp * 32 + lane] = acc.s;
@@ -680,17 +730,17 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
         // warp w (and w + 16) finishes column c0 + w: lanes 0..15 hold the per-warp partials
         for (int cw = warp; cw < 32; cw += kOcWarps) {
           const int jc = c0 + cw;
-          Lse<T> tot;
+          Lse2 tot;
           tot.m = (lane < kOcWarps) ? red_m[lane * 32 + cw] : -CUDART_INF_F;
           tot.s = (lane < kOcWarps) ? red_s[lane * 32 + cw] : 0.f;
-          warp_merge(tot);
+          warp_merge2(tot);
           if (lane == 0 && jc < col1) {
-            const float lse = tot.value();
+            const float lse2 = tot.value();
             if (check) {
-              const double d = (double)__expf(__ldcg(lv_buf + (int64_t)cur * J + jc) + lse) - (double)b[jc];
+              const double d = (double)ex2f(__ldcg(lv_buf + (int64_t)cur * J + jc) + lse2) - (double)b[jc];
               atomicAdd(&err_s, d * d);
             }
-            lv_buf[(int64_t)nxt * J + jc] = log_b[jc] - lse;
+            lv_buf[(int64_t)nxt * J + jc] = log_b[jc] * kLog2e - lse2;
           }
         }
       }
@@ -712,54 +762,87 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
       float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
       if (gok[0]) v0 = __ldcg(src + gq[0]);
       if (gok[1]) v1 = __ldcg(src + gq[1]);
+      if (timer) st->t_phase[5] += gtime() - t4;
       if (gok[0]) reinterpret_cast<float4*>(lv_s)[gq[0]] = v0;
       if (gok[1]) reinterpret_cast<float4*>(lv_s)[gq[1]] = v1;
       // register rows: this thread's columns of rows S..R-1 (it already holds the matching log v values)
-      Lse<T> racc[kOcRR];
 #pragma unroll
       for (int rr = 0; rr < kOcRR; ++rr) {
-        racc[rr].init();
-        if (gok[0])
-          racc[rr].push4(fmaf(-mreg[rr][0].x, inv_reg, v0.x), fmaf(-mreg[rr][0].y, inv_reg, v0.y),
-                         fmaf(-mreg[rr][0].z, inv_reg, v0.z), fmaf(-mreg[rr][0].w, inv_reg, v0.w));
-        if (gok[1])
-          racc[rr].push4(fmaf(-mreg[rr][1].x, inv_reg, v1.x), fmaf(-mreg[rr][1].y, inv_reg, v1.y),
-                         fmaf(-mreg[rr][1].z, inv_reg, v1.z), fmaf(-mreg[rr][1].w, inv_reg, v1.w));
-        warp_merge(racc[rr]);
-        if (lane == 0) { rr_m[warp * 8 + rr] = racc[rr].m; rr_s[warp * 8 + rr] = racc[rr].s; }
+        float z[8];
+        z[0] = gok[0] ? fmaf(-mreg[rr][0].x, inv2, v0.x) : -CUDART_INF_F;
+        z[1] = gok[0] ? fmaf(-mreg[rr][0].y, inv2, v0.y) : -CUDART_INF_F;
+        z[2] = gok[0] ? fmaf(-mreg[rr][0].z, inv2, v0.z) : -CUDART_INF_F;
+        z[3] = gok[0] ? fmaf(-mreg[rr][0].w, inv2, v0.w) : -CUDART_INF_F;
+        z[4] = gok[1] ? fmaf(-mreg[rr][1].x, inv2, v1.x) : -CUDART_INF_F;
+        z[5] = gok[1] ? fmaf(-mreg[rr][1].y, inv2, v1.y) : -CUDART_INF_F;
+        z[6] = gok[1] ? fmaf(-mreg[rr][1].z, inv2, v1.z) : -CUDART_INF_F;
+        z[7] = gok[1] ? fmaf(-mreg[rr][1].w, inv2, v1.w) : -CUDART_INF_F;
+        float mx = fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(z[6], z[7])));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float ref = (mx == -CUDART_INF_F) ? 0.f : mx;
+        float sum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += ex2f(z[e] - ref);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) { rr_m[warp * 8 + rr] = mx; rr_s[warp * 8 + rr] = sum; }
       }
     }
+    if (timer) st->t_phase[6] += gtime() - t4;
     __syncthreads();
     {
       const float4* pv = reinterpret_cast<const float4*>(lv_s);
       for (int r = warp; r < S; r += kOcWarps) {
         const float4* mrow = m_res + r * ng;
-        Lse<T> acc[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u].init();
-        for (int g0 = lane; g0 < ng; g0 += 32 * 4) {
+        // ONE pass (shared-memory bandwidth is what binds here: every warp streams its row and the whole log v):
+        // 16 elements per step, one rescale of the running sum per step, then 16 ex2.
+        float run_m = -CUDART_INF_F, run_s = 0.f;
+        for (int g0 = lane; g0 < ng; g0 += 128) {
+          float z[16];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int g = g0 + 32 * u;
             if (g < ng) {
               const float4 e = mrow[g], l = pv[g];
-              acc[u].push4(fmaf(-e.x, inv_reg, l.x), fmaf(-e.y, inv_reg, l.y), fmaf(-e.z, inv_reg, l.z),
-                           fmaf(-e.w, inv_reg, l.w));
+              z[4 * u + 0] = fmaf(-e.x, inv2, l.x); z[4 * u + 1] = fmaf(-e.y, inv2, l.y);
+              z[4 * u + 2] = fmaf(-e.z, inv2, l.z); z[4 * u + 3] = fmaf(-e.w, inv2, l.w);
+            } else {
+              z[4 * u + 0] = z[4 * u + 1] = z[4 * u + 2] = z[4 * u + 3] = -CUDART_INF_F;
             }
           }
-        }
-        acc[0].merge(acc[1].m, acc[1].s);
-        acc[2].merge(acc[3].m, acc[3].s);
-        acc[0].merge(acc[2].m, acc[2].s);
-        warp_merge(acc[0]);
-        if (lane == 0) lu_s[r] = log_a[row0 + r] - acc[0].value();
-      }
-      if (warp == 0 && lane < kOcRR && S + lane < R) {       // finish the register rows: 16 per-warp partials each
-        Lse<T> tot;
-        tot.init();
+          float mxl = run_m;
 #pragma unroll
-        for (int w = 0; w < kOcWarps; ++w) tot.merge(rr_m[w * 8 + lane], rr_s[w * 8 + lane]);
-        lu_s[S + lane] = log_a[row0 + S + lane] - tot.value();
+          for (int e = 0; e < 16; ++e) mxl = fmaxf(mxl, z[e]);
+          const float refl = (mxl == -CUDART_INF_F) ? 0.f : mxl;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            a0 += ex2f(z[e] - refl); a1 += ex2f(z[e + 1] - refl); a2 += ex2f(z[e + 2] - refl); a3 += ex2f(z[e + 3] - refl);
+          }
+          run_s = run_s * ex2f(run_m - refl) + ((a0 + a1) + (a2 + a3));
+          run_m = mxl;
+        }
+        float mx = run_m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float ref = (mx == -CUDART_INF_F) ? 0.f : mx;
+        const float s0 = run_s * ex2f(run_m - ref), s1 = 0.f;
+        float sum = s0 + s1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) lu_s[r] = log_a[row0 + r] * kLog2e - (mx + lg2f(sum));
+      }
+      if (timer) st->t_phase[7] += gtime() - t4;
+      if (warp == kOcWarps - 1) {                            // finish the register rows: 16 per-warp partials each
+#pragma unroll
+        for (int rr = 0; rr < kOcRR; ++rr) {
+          Lse2 tot;
+          tot.m = (lane < kOcWarps) ? rr_m[lane * 8 + rr] : -CUDART_INF_F;
+          tot.s = (lane < kOcWarps) ? rr_s[lane * 8 + rr] : 0.f;
+          warp_merge2(tot);
+          if (lane == 0 && S + rr < R) lu_s[S + rr] = log_a[row0 + S + rr] * kLog2e - tot.value();
+        }
       }
     }
     __syncthreads();
@@ -770,8 +853,8 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
     }
   }
   if (!stopped) final_buf = max_iter & 1;
-  for (int r = tid; r < R; r += kOcThreads) log_u_out[row0 + r] = lu_s[r];
-  for (int j = col0 + tid; j < col1; j += kOcThreads) log_v_out[j] = __ldcg(lv_buf + (int64_t)final_buf * J + j);
+  for (int r = tid; r < R; r += kOcThreads) log_u_out[row0 + r] = lu_s[r] * kLn2;
+  for (int j = col0 + tid; j < col1; j += kOcThreads) log_v_out[j] = __ldcg(lv_buf + (int64_t)final_buf * J + j) * kLn2;
   if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = final_buf; st->err = err; }
 }
 
@@ -839,7 +922,7 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
         const int TB = 256;
         log_kernel<T><<<(unsigned)ceil_div(I, TB), TB, 0, s>>>(a, I, w.log_a); EG_LAUNCHED();
         log_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(b, J, w.log_b); EG_LAUNCHED();
-        fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log((double)J))); EG_LAUNCHED();
+        fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log2((double)J))); EG_LAUNCHED();
         EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
         float inv_reg = (float)(1.0 / reg);
         int64_t ld = J;
@@ -858,10 +941,11 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
         if (getenv("EG_PERSIST_TIMING")) {
           PersistState full;
           cudaMemcpy(&full, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost);
-          fprintf(stderr, "[eagraft] on-chip sinkhorn (S=%d): %d sweeps; CTA0 us/sweep: C %.2f | bar %.2f | R %.2f | bar %.2f | U %.2f\n",
+          fprintf(stderr, "[eagraft] on-chip sinkhorn (S=%d): %d sweeps; CTA0 us/sweep: C %.2f | bar %.2f | R %.2f | bar %.2f | U %.2f (lv loaded %.2f, reg rows %.2f, smem row %.2f)\n",
                   S_max, full.sweeps, full.t_phase[0] / 1e3 / full.sweeps, full.t_phase[1] / 1e3 / full.sweeps,
                   full.t_phase[2] / 1e3 / full.sweeps, full.t_phase[3] / 1e3 / full.sweeps,
-                  full.t_phase[4] / 1e3 / full.sweeps);
+                  full.t_phase[4] / 1e3 / full.sweeps, full.t_phase[5] / 1e3 / full.sweeps,
+                  full.t_phase[6] / 1e3 / full.sweeps, full.t_phase[7] / 1e3 / full.sweeps);
         }
         *used = true;
         return EG_OK;
