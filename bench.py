@@ -337,6 +337,12 @@ def run_ours(args):
                             "DRAM traffic is ~one read of M. Its binding unit is MUFU + grid barriers: exp throughput "
                             "= %.2f of the 148*16/clk MUFU peak." % ((sum(sk_exps) / (sum(sk_ms) / 1e3) / mufu_peak) if sk_ms else 0.0)}
     roofline_dom["frac"] = roofline_dom["achieved"] / roofline_dom["peak"]
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "sinkhorn_onchip_traffic.json")))
+        roofline_dom["traffic"] = tj.get("dram_bytes_per_launch")
+        roofline_dom["traffic_source"] = tj.get("source")
+    except Exception:
+        pass
     roofline = {"kernel": "spmm_vec_kernel<3,2,4> (fused SpMM fwd + transposed bwd, d=300)", "bound": "hbm",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
