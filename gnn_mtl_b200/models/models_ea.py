@@ -43,21 +43,13 @@ class BaseModel(nn.Module):
 
 
 def _margin_loss(outputs, ILL, neg_left, neg_right, neg2_left, neg2_right, k):
-    """Margin-based L1 ranking loss with hard negatives (:103-123 / :185-204);
-    plain tensor algebra — SURVEY.md §8f rank 1, not a changed subsystem yet."""
-    t = len(ILL)
-    dev = outputs.device
-
-    def ix(a):
-        return torch.as_tensor(np.asarray(a, dtype=np.int64), device=dev)
-
-    A = torch.sum(torch.abs(outputs[ix(ILL[:, 0])] - outputs[ix(ILL[:, 1])]), 1)
-    D = A + 1.0
-    B = torch.sum(torch.abs(outputs[ix(neg_left)] - outputs[ix(neg_right)]), 1)
-    L1 = F.relu(torch.add(-torch.reshape(B, [t, k]), torch.reshape(D, [t, 1])))
-    B = torch.sum(torch.abs(outputs[ix(neg2_left)] - outputs[ix(neg2_right)]), 1)
-    L2 = F.relu(torch.add(-torch.reshape(B, [t, k]), torch.reshape(D, [t, 1])))
-    return (torch.sum(L1) + torch.sum(L2)) / (2.0 * t * k)
+    """Margin-based L1 ranking loss with hard negatives (:103-123 / :185-204) on the fused
+    gather + L1 + hinge kernel (eg_margin_loss_fwd/bwd); the reference's index arrays are float
+    NumPy arrays of integral values — they are cast to int64 here."""
+    ILL = np.asarray(ILL)
+    return ops.margin_loss(outputs, np.asarray(ILL[:, 0], dtype=np.int64), np.asarray(ILL[:, 1], dtype=np.int64),
+                           np.asarray(neg_left, dtype=np.int64), np.asarray(neg_right, dtype=np.int64),
+                           np.asarray(neg2_left, dtype=np.int64), np.asarray(neg2_right, dtype=np.int64), k, 1.0)
 
 
 class EAModel(BaseModel):

@@ -346,3 +346,42 @@ def gemm_nt(A_parts, B, bias=None, n1=None):
                                     ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
               "eg_gemm_nt_3xtf32")
     return (out1, out2) if out2 is not None else out1
+
+
+# ---- margin ranking loss (fused gather + L1 + hinge) --------------------------------------------
+
+class _MarginLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outputs, left, right, nl, nr, n2l, n2r, k, gamma):
+        out = _f32c(outputs)
+        t = int(left.numel())
+        loss = torch.zeros(1, dtype=torch.float64, device=out.device)
+        with torch.cuda.device(out.device):
+            check(lib.eg_margin_loss_fwd(ptr(out), out.shape[0], out.shape[1], ptr(left), ptr(right), ptr(nl), ptr(nr),
+                                         ptr(n2l), ptr(n2r), t, int(k), float(gamma), ptr(loss), stream()),
+                  "eg_margin_loss_fwd")
+        ctx.save_for_backward(out, left, right, nl, nr, n2l, n2r)
+        ctx.k, ctx.gamma, ctx.t = int(k), float(gamma), t
+        return (loss[0] / (2.0 * t * k)).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        out, left, right, nl, nr, n2l, n2r = ctx.saved_tensors
+        grad = torch.zeros_like(out)
+        scale = float(g) / (2.0 * ctx.t * ctx.k)
+        with torch.cuda.device(out.device):
+            check(lib.eg_margin_loss_bwd(ptr(out), out.shape[0], out.shape[1], ptr(left), ptr(right), ptr(nl), ptr(nr),
+                                         ptr(n2l), ptr(n2r), ctx.t, ctx.k, ctx.gamma, scale, ptr(grad), stream()),
+                  "eg_margin_loss_bwd")
+        return grad, None, None, None, None, None, None, None, None
+
+
+def margin_loss(outputs, left, right, nl, nr, n2l, n2r, k, gamma=1.0):
+    """(sum relu(A+gamma-B1) + sum relu(A+gamma-B2)) / (2 t k) — models/models_ea.py:103-123."""
+    _lib.require_cuda(outputs)
+    dev = outputs.device
+
+    def ix(a):
+        a = a if torch.is_tensor(a) else torch.as_tensor(a)
+        return a.to(device=dev, dtype=torch.int64).contiguous()
+    return _MarginLoss.apply(outputs, ix(left), ix(right), ix(nl), ix(nr), ix(n2l), ix(n2r), k, gamma)

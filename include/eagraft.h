@@ -201,6 +201,19 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
                       const float* B_hi, const float* B_lo, int64_t n, const float* bias,
                       float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
 
+/* ---- margin-based L1 ranking loss with hard negatives -------------
+ * Replaces the four [t*k, d] gathers + abs/sum/relu of models/models_ea.py:103-123,185-204:
+ *   *loss_sum = sum_{p<t, q<k} relu(A_p + gamma - |out[nl]-out[nr]|_1) + relu(A_p + gamma - |out[n2l]-out[n2r]|_1),
+ *   A_p = |out[left_p] - out[right_p]|_1     (the caller divides by 2*t*k).  Index arrays are int64,
+ * negatives are laid out [t, k] row-major.  eg_margin_loss_bwd ADDS scale * d(loss_sum)/d(out) into
+ * grad [n, d] (caller zeroes it); the sub-gradient of |.| at 0 is 0, as torch.abs.  d <= 512 for bwd. */
+int eg_margin_loss_fwd(const float* out, int64_t n, int d, const int64_t* left, const int64_t* right,
+                       const int64_t* nl, const int64_t* nr, const int64_t* n2l, const int64_t* n2r,
+                       int64_t t, int k, float gamma, double* loss_sum, eg_stream_t stream);
+int eg_margin_loss_bwd(const float* out, int64_t n, int d, const int64_t* left, const int64_t* right,
+                       const int64_t* nl, const int64_t* nr, const int64_t* n2l, const int64_t* n2r,
+                       int64_t t, int k, float gamma, float scale, float* grad, eg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

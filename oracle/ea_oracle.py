@@ -393,3 +393,24 @@ def mutual_nearest_pairs(outputs, L_ids, R_ids, bsz):
     pairs = np.stack([keep, r_arg[keep]], 1)
     order = np.argsort(r_min[keep], kind="stable")[:bsz]
     return pairs[order]
+
+
+# --------------------------------------------------------------------------- #
+# §8f-1  margin ranking loss with hard negatives                               #
+# --------------------------------------------------------------------------- #
+
+
+def margin_loss(outputs, ILL, neg_left, neg_right, neg2_left, neg2_right, k, gamma=1.0):
+    """models/models_ea.py:103-123 (EAModel.get_loss) == :185-204 (UEAModel.get_loss):
+    A = |x_l - x_r|_1 per pair; hinge relu(A + gamma - |x_nl - x_nr|_1) over both negative sets;
+    mean over 2 t k."""
+    ILL = np.asarray(ILL)
+    t = len(ILL)
+
+    def ix(a):
+        return torch.as_tensor(np.asarray(a, dtype=np.int64))
+    A = (outputs[ix(ILL[:, 0])] - outputs[ix(ILL[:, 1])]).abs().sum(1)
+    D = (A + gamma).reshape(t, 1)
+    B1 = (outputs[ix(neg_left)] - outputs[ix(neg_right)]).abs().sum(1).reshape(t, k)
+    B2 = (outputs[ix(neg2_left)] - outputs[ix(neg2_right)]).abs().sum(1).reshape(t, k)
+    return (F.relu(D - B1).sum() + F.relu(D - B2).sum()) / (2.0 * t * k)

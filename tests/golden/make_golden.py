@@ -142,7 +142,31 @@ def eval_fixture():
              T=T.numpy(), gw_keys=np.array(list(gw.keys())), gw_vals=np.array(list(gw.values())))
 
 
+def margin_fixture():
+    """EAModel.get_loss of the live reference (models/models_ea.py:103-123) on integer index arrays
+    (the reference builds them as float arrays of integral values, which current torch refuses as indices)."""
+    rng = np.random.default_rng(33)
+    n, d, t, k = 120, 20, 25, 6
+    out = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32) * 0.4).requires_grad_(True)
+    ILL = np.stack([rng.permutation(60)[:t], rng.permutation(60)[:t] + 60], 1).astype(np.int64)
+
+    class _Fake:
+        pass
+    me = _Fake()
+    me.neg_num = k
+    me.neg_left = np.repeat(ILL[:, 0], k)
+    me.neg2_right = np.repeat(ILL[:, 1], k)
+    me.neg_right = rng.integers(0, n, t * k)
+    me.neg2_left = rng.integers(0, n, t * k)
+    loss = ref.models_ea.EAModel.get_loss(me, out, {"train": ILL}, "train")
+    loss.backward()
+    np.savez(os.path.join(HERE, "margin.npz"), out=out.detach().numpy(), ILL=ILL, k=k, neg_left=me.neg_left,
+             neg_right=me.neg_right, neg2_left=me.neg2_left, neg2_right=me.neg2_right,
+             loss=loss.detach().numpy(), grad=out.grad.numpy())
+
+
 if __name__ == "__main__":
+    margin_fixture()
     n_ent, KG, adj = adjacency_fixture()
     layer_fixture(n_ent, adj)
     sinkhorn_fixture()

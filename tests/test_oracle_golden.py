@@ -110,3 +110,12 @@ def test_eval_entry_points(golden_dir):
     a = orc.diagonal_ranks(sim)
     b = orc.diagonal_ranks_by_sort(sim)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_margin_loss(golden_dir):
+    g = _load(golden_dir, "margin.npz")
+    out = torch.from_numpy(g["out"]).requires_grad_(True)
+    loss = orc.margin_loss(out, g["ILL"], g["neg_left"], g["neg_right"], g["neg2_left"], g["neg2_right"], int(g["k"]))
+    loss.backward()
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
+    np.testing.assert_allclose(out.grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
