@@ -78,3 +78,33 @@ def make_powerlaw_graph(n_nodes, avg_degree, seed=0, zipf=1.0):
     heads = _zipf_sample(rng, n_nodes, n_triples, zipf)
     tails = rng.integers(0, n_nodes, n_triples)
     return heads.astype(np.int64), tails.astype(np.int64)
+
+
+def write_dbp15k_dir(kg, root, lang="zh_en"):
+    """Write a synthetic pair in the DBP15K on-disk layout the reference reads
+    (utils/data_utils.py:375-384: ent_ids_{1,2}, rel_ids_{1,2}, triples_{1,2}, ref_ent_ids, ref_r_ids,
+    <lang[:2]>_vectorList.json).  Returns the directory."""
+    import json
+    import os
+    d = os.path.join(root, lang)
+    os.makedirs(d, exist_ok=True)
+    e1 = kg["e1"]
+    tri = kg["triples"]
+    kg1, kg2 = tri[tri[:, 0] < e1], tri[tri[:, 0] >= e1]
+    rels1, rels2 = sorted(set(kg1[:, 1].tolist())), sorted(set(kg2[:, 1].tolist()))
+
+    def dump(name, rows):
+        with open(os.path.join(d, name), "w", encoding="utf-8") as f:
+            for r in rows:
+                f.write("\t".join(str(c) for c in r) + "\n")
+    dump("ent_ids_1", [(i, "e%d" % i) for i in range(e1)])
+    dump("ent_ids_2", [(i, "e%d" % i) for i in range(e1, kg["n"])])
+    dump("rel_ids_1", [(r, "r%d" % r) for r in rels1])
+    dump("rel_ids_2", [(r, "r%d" % r) for r in rels2])
+    dump("triples_1", kg1.tolist())
+    dump("triples_2", kg2.tolist())
+    dump("ref_ent_ids", kg["links"].tolist())
+    dump("ref_r_ids", [(rels1[0], rels2[0])])
+    with open(os.path.join(d, lang[0:2] + "_vectorList.json"), "w", encoding="utf-8") as f:
+        json.dump([[float(v) for v in row] for row in kg["x"]], f)
+    return d

@@ -70,3 +70,32 @@ def test_hits_and_negatives_medium():
         n_nodes, device = 700, "cpu"
     neg = ref_shim.ref.models_ea.BaseModel(_A()).get_neg(pairs[:50, 0], vec, 25)
     assert np.array_equal(neg, orc.nearest_negatives(pairs[:50, 0], vec, 25))
+
+
+def test_dbp15k_loader_host_part_matches_reference(tmp_path, monkeypatch):
+    """§8f rank 2: the on-disk DBP15K layout parsed by read_dbp15k()/_split_links() vs the reference's
+    load_data_ea (utils/data_utils.py:375-413) on a synthetic directory."""
+    import types
+    import warnings
+    from gnn_mtl_b200.synth import make_kg_pair, write_dbp15k_dir
+    from gnn_mtl_b200.utils import data_utils as mine
+    kg = make_kg_pair("tiny", dim=12)
+    write_dbp15k_dir(kg, str(tmp_path / "data" / "dbp15k"), "zh_en")
+    monkeypatch.chdir(tmp_path)
+    args = types.SimpleNamespace(dataset="zh_en", model="HGCN", task="ea")
+    np.random.seed(7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_shim.ref.data_utils.load_data_ea(args)
+    np.random.seed(7)
+    raw = mine.read_dbp15k("zh_en", "data/dbp15k")
+    train, test = mine._split_links(raw["ill"])
+    assert np.array_equal(train, ref["train"]) and np.array_equal(test, ref["test"])
+    assert raw["kg1"] + raw["kg2"] == ref["triple"]
+    assert torch.allclose(raw["x"], ref["x"].to_dense(), atol=1e-7)
+    head, tail, head_r, tail_r = mine.rfunc(kg["n"], ref["triple"])
+    assert head == ref["head"] and tail == ref["tail"]
+    assert np.array_equal(head_r.toarray(), ref["head_r"]) and np.array_equal(tail_r.toarray(), ref["tail_r"])
+    crow, col, val = orc.adjacency_csr(kg["n"], np.array(ref["triple"])[:, 0], np.array(ref["triple"])[:, 2])
+    csr = ref["adj"].coalesce().to_sparse_csr()
+    assert np.array_equal(csr.crow_indices().numpy(), crow) and np.array_equal(csr.values().numpy(), val)
