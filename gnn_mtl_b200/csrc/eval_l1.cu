@@ -24,7 +24,7 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
                double* __restrict__ D, int64_t ldD) {
   __shared__ __align__(16) double Ls[kKC][kPad];
   __shared__ __align__(16) double Rs[kKC][kPad];
-  const int tx = threadIdx.x & 15;   // column group: j = j0 + 4*tx .. +3
+  const int tx = threadIdx.x & 15;   // columns j0 + 2*tx + {0,1} and j0 + 32 + 2*tx + {0,1}: 16-byte lane stride -> conflict-free LDS.128
   const int ty = threadIdx.x >> 4;   // row group:    i = i0 + 4*ty .. +3
   const int64_t i0 = (int64_t)blockIdx.y * kTile;
   const int64_t j0 = (int64_t)blockIdx.x * kTile;
@@ -34,31 +34,36 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
 
+  // staging: thread t owns element (row = t / 32 + 8*r, k = t % 32) of both tiles — coalesced along k.
+  // The NEXT chunk's global loads are issued before the current chunk's DADDs so their latency is hidden.
+  const int kk = threadIdx.x & 31;
+  const int rbase = threadIdx.x >> 5;
+  float lreg[kTile / 8], rreg[kTile / 8];
+  auto fetch = [&](int k0) {
+    const int kc = min(kKC, d - k0);
+#pragma unroll
+    for (int r = 0; r < kTile / 8; ++r) {
+      const int row = rbase + 8 * r;
+      lreg[r] = (kk < kc && i0 + row < nL) ? __ldg(L + (i0 + row) * d + k0 + kk) : 0.f;
+      rreg[r] = (kk < kc && j0 + row < nR) ? __ldg(R + (j0 + row) * d + k0 + kk) : 0.f;
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < d; k0 += kKC) {
     const int kc = min(kKC, d - k0);
-    // stage: thread t loads element (row = t / 32 + 8*r, k = t % 32): coalesced along k
-    {
-      const int kk = threadIdx.x & 31;
-      const int rbase = threadIdx.x >> 5;
 #pragma unroll
-      for (int r = 0; r < kTile / 8; ++r) {
-        int row = rbase + 8 * r;
-        float lv = 0.f, rv = 0.f;
-        if (kk < kc) {
-          if (i0 + row < nL) lv = __ldg(L + (i0 + row) * d + k0 + kk);
-          if (j0 + row < nR) rv = __ldg(R + (j0 + row) * d + k0 + kk);
-        }
-        Ls[kk][row] = (double)lv;
-        Rs[kk][row] = (double)rv;
-      }
+    for (int r = 0; r < kTile / 8; ++r) {
+      Ls[kk][rbase + 8 * r] = (double)lreg[r];
+      Rs[kk][rbase + 8 * r] = (double)rreg[r];
     }
     __syncthreads();
+    if (k0 + kKC < d) fetch(k0 + kKC);
 #pragma unroll 4
     for (int k = 0; k < kc; ++k) {
       const double2 l01 = *reinterpret_cast<const double2*>(&Ls[k][4 * ty]);
       const double2 l23 = *reinterpret_cast<const double2*>(&Ls[k][4 * ty + 2]);
-      const double2 r01 = *reinterpret_cast<const double2*>(&Rs[k][4 * tx]);
-      const double2 r23 = *reinterpret_cast<const double2*>(&Rs[k][4 * tx + 2]);
+      const double2 r01 = *reinterpret_cast<const double2*>(&Rs[k][2 * tx]);
+      const double2 r23 = *reinterpret_cast<const double2*>(&Rs[k][32 + 2 * tx]);
       const double lv[4] = {l01.x, l01.y, l23.x, l23.y};
       const double rv[4] = {r01.x, r01.y, r23.x, r23.y};
 #pragma unroll
@@ -72,15 +77,16 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
   for (int a = 0; a < 4; ++a) {
     int64_t i = i0 + 4 * ty + a;
     if (i >= nL) continue;
-    int64_t j = j0 + 4 * tx;
-    double* dst = D + i * ldD + j;
-    if (j + 3 < nR && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-      reinterpret_cast<double2*>(dst)[0] = make_double2(acc[a][0], acc[a][1]);
-      reinterpret_cast<double2*>(dst)[1] = make_double2(acc[a][2], acc[a][3]);
-    } else {
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (j + b < nR) dst[b] = acc[a][b];
+    for (int h = 0; h < 2; ++h) {
+      const int64_t j = j0 + 32 * h + 2 * tx;
+      double* dst = D + i * ldD + j;
+      if (j + 1 < nR && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        *reinterpret_cast<double2*>(dst) = make_double2(acc[a][2 * h], acc[a][2 * h + 1]);
+      } else {
+        if (j < nR) dst[0] = acc[a][2 * h];
+        if (j + 1 < nR) dst[1] = acc[a][2 * h + 1];
+      }
     }
   }
 }
