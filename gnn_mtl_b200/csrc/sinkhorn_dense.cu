@@ -560,7 +560,8 @@ sinkhorn_persistent_kernel(const T* __restrict__ M, int64_t I, int64_t J, int64_
 constexpr int kOcThreads = 512;
 constexpr int kOcWarps = kOcThreads / 32;
 constexpr int kOcQ = 2;     // column groups (float4) per thread
-constexpr int kOcRR = 5;    // rows kept in registers
+constexpr int kOcRR = 5;    // rows kept in registers (phase C is written for exactly 4 + 1)
+static_assert(kOcRR == 5, "phase C unrolls the register rows as 4 + 1");
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -660,35 +661,50 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
     for (int q = 0; q < kOcQ; ++q) {
       if (!gok[q]) continue;
       const float4* sbase = m_res + gq[q];
+      // ONE pass over the on-chip rows, 4 rows per step per column: running max, one rescale, 4 ex2
       float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-#pragma unroll 4
-      for (int r = 0; r < S; ++r) {
-        const float4 mv = sbase[r * ng];
-        const float lu = lu_s[r];
-        mx[0] = fmaxf(mx[0], fmaf(-mv.x, inv2, lu)); mx[1] = fmaxf(mx[1], fmaf(-mv.y, inv2, lu));
-        mx[2] = fmaxf(mx[2], fmaf(-mv.z, inv2, lu)); mx[3] = fmaxf(mx[3], fmaf(-mv.w, inv2, lu));
-      }
+      float sum[4] = {0.f, 0.f, 0.f, 0.f};
+      auto step4 = [&](const float (&z)[4][4]) {
 #pragma unroll
-      for (int rr = 0; rr < kOcRR; ++rr) {
-        const float lu = lu_s[S + rr];                      // -inf beyond R (lu_s is padded to 32 entries)
-        mx[0] = fmaxf(mx[0], fmaf(-mreg[rr][q].x, inv2, lu)); mx[1] = fmaxf(mx[1], fmaf(-mreg[rr][q].y, inv2, lu));
-        mx[2] = fmaxf(mx[2], fmaf(-mreg[rr][q].z, inv2, lu)); mx[3] = fmaxf(mx[3], fmaf(-mreg[rr][q].w, inv2, lu));
-      }
-      float ref[4], sum[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int v = 0; v < 4; ++v) {
+          const float m4 = fmaxf(fmaxf(fmaxf(z[0][v], z[1][v]), fmaxf(z[2][v], z[3][v])), mx[v]);
+          const float ref = (m4 == -CUDART_INF_F) ? 0.f : m4;
+          sum[v] = sum[v] * ex2f(mx[v] - ref) +
+                   ((ex2f(z[0][v] - ref) + ex2f(z[1][v] - ref)) + (ex2f(z[2][v] - ref) + ex2f(z[3][v] - ref)));
+          mx[v] = m4;
+        }
+      };
+      for (int r0 = 0; r0 < S; r0 += 4) {
+        float z[4][4];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) ref[v] = (mx[v] == -CUDART_INF_F) ? 0.f : mx[v];
-#pragma unroll 4
-      for (int r = 0; r < S; ++r) {
-        const float4 mv = sbase[r * ng];
-        const float lu = lu_s[r];
-        sum[0] += ex2f(fmaf(-mv.x, inv2, lu) - ref[0]); sum[1] += ex2f(fmaf(-mv.y, inv2, lu) - ref[1]);
-        sum[2] += ex2f(fmaf(-mv.z, inv2, lu) - ref[2]); sum[3] += ex2f(fmaf(-mv.w, inv2, lu) - ref[3]);
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          const float4 mv = (r < S) ? sbase[r * ng] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float lu = (r < S) ? lu_s[r] : -CUDART_INF_F;
+          z[u][0] = fmaf(-mv.x, inv2, lu); z[u][1] = fmaf(-mv.y, inv2, lu);
+          z[u][2] = fmaf(-mv.z, inv2, lu); z[u][3] = fmaf(-mv.w, inv2, lu);
+        }
+        step4(z);
       }
+      {
+        float z[4][4];
 #pragma unroll
-      for (int rr = 0; rr < kOcRR; ++rr) {
-        const float lu = lu_s[S + rr];
-        sum[0] += ex2f(fmaf(-mreg[rr][q].x, inv2, lu) - ref[0]); sum[1] += ex2f(fmaf(-mreg[rr][q].y, inv2, lu) - ref[1]);
-        sum[2] += ex2f(fmaf(-mreg[rr][q].z, inv2, lu) - ref[2]); sum[3] += ex2f(fmaf(-mreg[rr][q].w, inv2, lu) - ref[3]);
+        for (int rr = 0; rr < 4; ++rr) {
+          const float lu = lu_s[S + rr];                    // -inf beyond R (lu_s is padded to 32 entries)
+          z[rr][0] = fmaf(-mreg[rr][q].x, inv2, lu); z[rr][1] = fmaf(-mreg[rr][q].y, inv2, lu);
+          z[rr][2] = fmaf(-mreg[rr][q].z, inv2, lu); z[rr][3] = fmaf(-mreg[rr][q].w, inv2, lu);
+        }
+        step4(z);
+        const float lu = lu_s[S + 4];
+        const float z4[4] = {fmaf(-mreg[4][q].x, inv2, lu), fmaf(-mreg[4][q].y, inv2, lu),
+                             fmaf(-mreg[4][q].z, inv2, lu), fmaf(-mreg[4][q].w, inv2, lu)};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float m4 = fmaxf(z4[v], mx[v]);
+          const float ref = (m4 == -CUDART_INF_F) ? 0.f : m4;
+          sum[v] = sum[v] * ex2f(mx[v] - ref) + ex2f(z4[v] - ref);
+          mx[v] = m4;
+        }
       }
       reinterpret_cast<float4*>(part_m + (int64_t)cta * J)[gq[q]] = make_float4(mx[0], mx[1], mx[2], mx[3]);
       reinterpret_cast<float4*>(part_s + (int64_t)cta * J)[gq[q]] = make_float4(sum[0], sum[1], sum[2], sum[3]);
