@@ -1,0 +1,49 @@
+"""BASELINE.json config 4 at N GPUs: row-partitioned SpMM on a power-law graph, feature rows all-gathered
+over NCCL before each aggregation (forward and transposed backward).  Run under torchrun."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+if world > 1: dist.init_process_group("nccl", device_id=dev)
+from gnn_mtl_b200 import ops, parallel as par
+from gnn_mtl_b200.adjacency import DeviceAdjacency
+from gnn_mtl_b200.synth import make_powerlaw_graph
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+deg = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+h, t = make_powerlaw_graph(n, deg, seed=1)
+full = DeviceAdjacency.from_heads_tails(n, torch.from_numpy(h).to(dev), torch.from_numpy(t).to(dev))
+nnz = full.nnz
+sh = par.ShardedAdjacency(full) if world > 1 else None
+del h, t
+res = []
+for d in (128, 300):
+    H_local = torch.randn((sh.r1 - sh.r0) if sh else n, d, device=dev)
+    def fwd():
+        Hf = sh.gather(H_local) if sh else H_local
+        return ops.spmm(sh.csr if sh else full.csr, Hf)[0]
+    def bwd():
+        Hf = sh.gather(H_local) if sh else H_local
+        return ops.spmm(sh.csr_t if sh else full.csr_t, Hf)[0]
+    def gather_only():
+        return sh.gather(H_local) if sh else H_local
+    out = {}
+    for name, f in (("fwd", fwd), ("bwd", bwd), ("allgather", gather_only)):
+        for _ in range(2): f()
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): f()
+        e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 5], device=dev, dtype=torch.float64)
+        if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[name] = float(ms[0])
+    byt = nnz * 8 + (n + 1) * 4 + nnz * d * 4 + n * d * 4
+    res.append({"d": d, "fwd_ms": out["fwd"], "bwd_ms": out["bwd"], "allgather_ms": out["allgather"],
+                "fwd_gbs_aggregate": byt / out["fwd"] / 1e6, "bwd_gbs_aggregate": byt / out["bwd"] / 1e6,
+                "spmm_only_gbs_aggregate": byt / max(out["fwd"] - out["allgather"], 1e-6) / 1e6})
+if rank == 0:
+    print(json.dumps({"config": "row-partitioned SpMM, power-law graph n=%d target degree %d, nnz=%d" % (n, deg, nnz),
+                      "n_gpus": world, "results": res}))
+if world > 1: dist.destroy_process_group()
