@@ -89,6 +89,17 @@ class _Aggregate(torch.autograd.Function):
 USE_TCGEN05_GEMM = True   # dense layer products on the 3xTF32 tcgen05 tiles; False -> everything on cuBLAS fp32
 
 
+def _weight_grad(d_hidden, x):
+    """dW = dHᵀ·x ([out, n]·[n, in]) on cuBLAS fp32.  The plain call tiles only the 300x300 output
+    (15 CTAs on 148 SMs); batching the reduction dimension gives cuBLAS a split-K it does not pick itself."""
+    n = x.shape[0]
+    x = x.contiguous()
+    for parts in (64, 32, 16):
+        if n % parts == 0 and n // parts >= 1024:
+            return torch.bmm(d_hidden.view(parts, n // parts, -1).transpose(1, 2), x.view(parts, n // parts, -1)).sum(0)
+    return d_hidden.t() @ x
+
+
 class _DenseProducts(torch.autograd.Function):
     """hidden = x·Wᵀ + b  and (highway) gate_pre = x·G + c  (layers/layers.py:61,69).
 
@@ -130,7 +141,7 @@ class _DenseProducts(torch.autograd.Function):
             else:
                 dx = ops.gemm_nt([d_hidden], weight.t().contiguous())
         if ctx.needs_input_grad[1]:
-            dW = d_hidden.t() @ x
+            dW = _weight_grad(d_hidden.contiguous(), x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = d_hidden.sum(0)
         return dx, dW, db, None, None, None
