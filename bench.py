@@ -293,6 +293,24 @@ def run_ours(args):
            "note": "per-step host inputs are the two sampled index arrays (models_ea.py:211-212); "
                    "features/adjacency stay resident across steps as in the reference's own loop"}
 
+    # ---- stricter end-to-end variant: ALSO re-upload the 240 MB feature matrix from pinned host memory every step
+    # (the reference keeps it on the device across steps, run/train_unsup_ea.py:73-77; reported for completeness)
+    x_host = x.detach().cpu().pin_memory()
+    step(None)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        x.copy_(x_host, non_blocking=True)
+        loss = step(None)
+        _ = loss.item()
+    ev1.record()
+    barrier()
+    ms_cold = max_over_ranks(ev0.elapsed_time(ev1)) / K
+    e2e["with_feature_upload_every_step"] = {"value": world * 1e3 / ms_cold, "unit": UNIT, "ms_per_step": ms_cold,
+                                             "h2d_bytes_per_step": int(x_host.numel() * 4 + 2 * bsz * 8),
+                                             "d2h_bytes_per_step": 8}
+    del x_host
+
     # ---- roofline: per-launch CUDA-event timing of the SpMM kernel inside the same step ----
     ops.SPMM_TIMER = []
     ops.SINKHORN_TIMER = []
