@@ -9,6 +9,8 @@
 // (deterministic).  Hub rows of power-law graphs are cut into fixed-length
 // segments handled by extra warps; their partial sums are combined, in order,
 // by a second small launch that also applies the epilogue.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eg {
@@ -18,6 +20,7 @@ constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
 // Tuning knobs (defaults chosen from the ncu study in profiles/); eg_debug_set() overrides them.
 int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each)
 int g_tune_warps = 4;       // warps (= rows) per CTA
+int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelined SpMM with n CTAs per SM
 extern int g_tune_persistent;
 extern int g_tune_resident;
 extern int g_tune_onchip;
@@ -189,6 +192,118 @@ spmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
   }
 }
 
+// Persistent, software-pipelined variant: each warp walks work items w, w + stride, … and fetches the NEXT
+// item's bounds and first (col, val) chunk while the current item's feature-row gathers are in flight, so the
+// rowptr -> col/val -> feature-row dependency chain (three L2/HBM round trips for ~11 neighbours of work)
+// is paid once per warp instead of once per row.
+template <int VPL, int UNROLL>
+__device__ __forceinline__ void gather_chunk(const float4* __restrict__ Hc, int d4, int d4_local, int lane, int cnt,
+                                             int my_col, float my_val, const Policies& pol, float4 (&acc)[VPL]) {
+  for (int t = 0; t < cnt; t += UNROLL) {
+    float4 x[UNROLL][VPL];
+    float v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int c = __shfl_sync(0xffffffffu, my_col, (t + u) & 31);
+      float vv = __shfl_sync(0xffffffffu, my_val, (t + u) & 31);
+      bool live = (t + u < cnt);
+      v[u] = live ? vv : 0.f;
+      const float4* rowp = Hc + (int64_t)c * d4;
+#pragma unroll
+      for (int p = 0; p < VPL; ++p) {
+        int k = lane + 32 * p;
+        x[u][p] = (live && k < d4_local) ? ld_keep_f4(rowp + k, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+      for (int p = 0; p < VPL; ++p) {
+        acc[p].x = fmaf(v[u], x[u][p].x, acc[p].x);
+        acc[p].y = fmaf(v[u], x[u][p].y, acc[p].y);
+        acc[p].z = fmaf(v[u], x[u][p].z, acc[p].z);
+        acc[p].w = fmaf(v[u], x[u][p].w, acc[p].w);
+      }
+    }
+  }
+}
+
+template <int VPL, int UNROLL>
+__global__ void __launch_bounds__(256)
+spmm_persist_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const float* __restrict__ val, int64_t n_rows, const float* __restrict__ H, int d4,
+                    int chunk0, Epilogue ep, int thresh, const int32_t* __restrict__ seg_begin,
+                    const int32_t* __restrict__ seg_end, int64_t n_seg, float* __restrict__ seg_scratch,
+                    int hints) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  const int64_t total = n_rows + n_seg;
+  int64_t w = blockIdx.x * (int64_t)8 + (threadIdx.x >> 5);
+  if (w >= total) return;
+  const Policies pol = make_policies(hints != 0);
+  const float4* Hc = reinterpret_cast<const float4*>(H) + chunk0;
+  const int d4_local = min(d4 - chunk0, 32 * VPL);
+  auto bounds = [&](int64_t item, int& b, int& e) {
+    if (item < n_rows) {
+      b = __ldg(rowptr + item);
+      e = __ldg(rowptr + item + 1);
+      if (e - b > thresh) e = b - 1;            // long row: handled by its segments; marks "skip"
+    } else {
+      b = __ldg(seg_begin + (item - n_rows));
+      e = __ldg(seg_end + (item - n_rows));
+    }
+  };
+  int b, e;
+  bounds(w, b, e);
+  int my_col = 0;
+  float my_val = 0.f;
+  if (b + lane < e) { my_col = ld_stream_i32(col + b + lane); my_val = ld_stream_f32(val + b + lane); }
+  while (true) {
+    const int64_t wn = w + stride;
+    const bool has_next = wn < total;
+    int nb = 0, ne = 0;
+    if (has_next) bounds(wn, nb, ne);                        // independent loads, issued before the gathers
+    float4 acc[VPL];
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool skip = e < b;
+    if (!skip) {
+      gather_chunk<VPL, UNROLL>(Hc, d4, d4_local, lane, min(32, e - b), my_col, my_val, pol, acc);
+      for (int base = b + 32; base < e; base += 32) {
+        int c2 = 0;
+        float v2 = 0.f;
+        if (base + lane < e) { c2 = ld_stream_i32(col + base + lane); v2 = ld_stream_f32(val + base + lane); }
+        gather_chunk<VPL, UNROLL>(Hc, d4, d4_local, lane, min(32, e - base), c2, v2, pol, acc);
+      }
+    }
+    int ncol = 0;
+    float nval = 0.f;
+    if (has_next && nb + lane < ne) { ncol = ld_stream_i32(col + nb + lane); nval = ld_stream_f32(val + nb + lane); }
+    if (!skip) {
+      if (w < n_rows) {
+#pragma unroll
+        for (int p = 0; p < VPL; ++p) {
+          int k = lane + 32 * p;
+          if (k < d4_local) {
+            int64_t off4 = w * d4 + chunk0 + k;
+            float4 r = apply_epilogue(ep, acc[p], off4, pol);
+            st_once_f4(reinterpret_cast<float4*>(ep.out) + off4, r, pol);
+          }
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(seg_scratch) + (w - n_rows) * d4 + chunk0;
+#pragma unroll
+        for (int p = 0; p < VPL; ++p) {
+          int k = lane + 32 * p;
+          if (k < d4_local) dst[k] = acc[p];
+        }
+      }
+    }
+    if (!has_next) break;
+    w = wn; b = nb; e = ne; my_col = ncol; my_val = nval;
+  }
+}
+
 // Finish long rows: sum their segment partials in segment order, then epilogue.
 __global__ void spmm_long_finish_kernel(const int32_t* __restrict__ long_rows,
                                         const int32_t* __restrict__ long_first, int64_t n_long,
@@ -269,6 +384,14 @@ static int launch_vec3(const int32_t* rowptr, const int32_t* col, const float* v
                        const int32_t* seg_begin, const int32_t* seg_end, int64_t n_seg, float* seg_scratch,
                        cudaStream_t s) {
   int64_t warps = n_rows + n_seg;
+  if (g_tune_spmm_persist > 0) {
+    int64_t want = ceil_div(warps, 8);
+    unsigned pgrid = (unsigned)std::min<int64_t>(want, (int64_t)kNumSMs * g_tune_spmm_persist);
+    spmm_persist_kernel<VPL, UNROLL><<<pgrid, 256, 0, s>>>(rowptr, col, val, n_rows, H, d4, chunk0, ep, thresh,
+                                                           seg_begin, seg_end, n_seg, seg_scratch, g_tune_hints);
+    EG_LAUNCHED();
+    return EG_OK;
+  }
   unsigned grid = (unsigned)ceil_div(warps, WARPS);
   spmm_vec_kernel<VPL, UNROLL, WARPS><<<grid, WARPS * 32, 0, s>>>(rowptr, col, val, n_rows, H, d4, chunk0, ep,
                                                                    thresh, seg_begin, seg_end, n_seg,
@@ -304,6 +427,7 @@ int eg_debug_set(int key, int value) {
   else if (key == 3) eg::g_tune_persistent = value;
   else if (key == 4) eg::g_tune_resident = value;
   else if (key == 5) eg::g_tune_onchip = value;
+  else if (key == 6) eg::g_tune_spmm_persist = value;
   else return EG_ERR_INVALID;
   return EG_OK;
 }

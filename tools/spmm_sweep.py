@@ -24,10 +24,11 @@ def bench(f, n=10):
     ts.sort(); return ts[len(ts) // 2]
 dbg = _lib.lib.eg_debug_set
 print("n=%d nnz=%d alg bytes plain %.2f GB fused %.2f GB" % (c.n_rows, c.nnz, byt / 1e9, (byt + 3 * c.n_rows * d * 4) / 1e9))
-for hints in (0, 1):
-    for unroll, warps in ((4, 8), (2, 8), (1, 8), (4, 4), (2, 4), (8, 4)):
-        dbg(0, unroll); dbg(1, warps); dbg(2, hints)
+for persist in (0, 2, 3, 4, 6):
+  for hints in (0,):
+    for unroll, warps in ((2, 4), (4, 4), (1, 8)) if persist else ((2, 4),):
+        dbg(0, unroll); dbg(1, warps); dbg(2, hints); dbg(6, persist)
         t1 = bench(lambda: ops.spmm(c, H))
         t2 = bench(lambda: ops.spmm(c, H, _lib.ACT_RELU, g, xr, True))
-        print("hints %d unroll %d warps %d | plain %.3f ms %5.0f GB/s | fused+save %.3f ms %5.0f GB/s" %
-              (hints, unroll, warps, t1, byt / t1 / 1e6, t2, (byt + 3 * c.n_rows * d * 4) / t2 / 1e6))
+        print("persist %d hints %d unroll %d warps %d | plain %.3f ms %5.0f GB/s | fused+save %.3f ms %5.0f GB/s" %
+              (persist, hints, unroll, warps, t1, byt / t1 / 1e6, t2, (byt + 3 * c.n_rows * d * 4) / t2 / 1e6))
