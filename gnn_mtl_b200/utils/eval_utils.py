@@ -41,8 +41,15 @@ def _hits_dict(rank_row, rank_col, top_k, n):
     return metrics
 
 
-def get_hits(vec, test_pair, top_k=(1, 10, 50, 100), *, return_ranks=False):
-    """Hits@k in both directions over the fp64 L1 matrix of the test pairs."""
+def mean_reciprocal_rank(rank_row, rank_col):
+    """MRR in both directions from the 0-based ranks (the reference has no MRR — BASELINE.json's north_star asks
+    for it; it falls out of the same rank computation): mean of 1 / (rank + 1)."""
+    return {"MRR_l": float((1.0 / (rank_row.double() + 1.0)).mean()), "MRR_r": float((1.0 / (rank_col.double() + 1.0)).mean())}
+
+
+def get_hits(vec, test_pair, top_k=(1, 10, 50, 100), *, return_ranks=False, mrr=False):
+    """Hits@k in both directions over the fp64 L1 matrix of the test pairs (keyword-only extras:
+    ``mrr=True`` appends MRR_l / MRR_r, ``return_ranks=True`` also returns the rank tensors)."""
     vec = _to_cuda(vec.detach())
     left, right = _pair_index(test_pair, vec.device)
     n = int(left.numel())
@@ -50,6 +57,8 @@ def get_hits(vec, test_pair, top_k=(1, 10, 50, 100), *, return_ranks=False):
     R = vec.index_select(0, right).to(torch.float32)
     rank_row, rank_col = ops.l1_ranks(L, R)
     metrics = _hits_dict(rank_row, rank_col, top_k, n)
+    if mrr:
+        metrics.update(mean_reciprocal_rank(rank_row, rank_col))
     if return_ranks:
         return metrics, rank_row, rank_col
     return metrics

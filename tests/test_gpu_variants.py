@@ -171,3 +171,17 @@ def test_drivers_end_to_end_on_dbp15k_layout(tmp_path, dev):
     args = make_args(model="GCN", epochs=4, neg_num=5, dim=32, min_epochs=2, data_root=root)
     model, metrics = train_ea(args, log=quiet)
     assert metrics["Hits@1_l"] >= 0
+
+
+def test_mrr_from_ranks(dev):
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200.utils.eval_utils import get_hits
+    rng = np.random.default_rng(4)
+    vec = rng.standard_normal((400, 16)).astype(np.float32)
+    pairs = np.stack([np.arange(150), np.arange(150) + 200], 1)
+    vec[pairs[:, 1]] = vec[pairs[:, 0]] + 0.9 * rng.standard_normal((150, 16)).astype(np.float32)
+    m = get_hits(torch.from_numpy(vec).to(dev), pairs, top_k=(1, 10), mrr=True)
+    rr, cr = orc.diagonal_ranks(orc.l1_matrix(vec[pairs[:, 0]], vec[pairs[:, 1]]))
+    assert abs(m["MRR_l"] - float(np.mean(1.0 / (rr + 1)))) < 1e-12
+    assert abs(m["MRR_r"] - float(np.mean(1.0 / (cr + 1)))) < 1e-12
+    assert list(m.keys()) == ["Hits@1_l", "Hits@10_l", "Hits@1_r", "Hits@10_r", "MRR_l", "MRR_r"]
