@@ -142,6 +142,30 @@ class UEAModel(BaseModel):
         return torch.sum(M[:, 0].to(torch.float64))
 
 
+def _gw_loss(self, outputs, data, bsz, *, max_iter=1000, epsilon=0.01, sample=None):
+    """models/models_ea.py:226-244 (call sites are commented out upstream, run/train_unsup_ea.py:100): L1 cost,
+    Gromov-Wasserstein plan by iterative projection, then — same quirk as the Wasserstein loss — the one-hot is
+    taken from argmax of a zero tensor, so the value is sum_i ||X_i - Y_0||_1."""
+    from ..SinkhornOT import gw_iterative_1
+    dev = outputs.device
+    if sample is None:
+        e1, e2 = data['e1'], data['e2']
+        index1, index2 = data['index1'], data['index2']
+        L = np.array([index1[i] for i in np.random.permutation(e1)[:bsz]])
+        R = np.array([index2[i] for i in np.random.permutation(e2)[:bsz]])
+        sample = (_host_to_device(L, dev), _host_to_device(R, dev))
+    X, Y = outputs[sample[0]], outputs[sample[1]]
+    a, b = torch.ones(bsz, device=dev), torch.ones(bsz, device=dev)
+    M = torch.cdist(X, Y, p=1)
+    C1 = torch.cdist(X, X, p=1).detach()
+    C2 = torch.cdist(Y, Y, p=1).detach()
+    gw_iterative_1(C1, C2, a, b, epsilon=epsilon, max_iter=max_iter)
+    return torch.sum(M[:, 0].to(torch.float64))
+
+
+UEAModel.get_loss_gromove_wassertein = _gw_loss
+
+
 def _host_to_device(arr, dev):
     """Host index array -> CUDA tensor through pinned memory (async H2D)."""
     staged = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).pin_memory()

@@ -414,3 +414,28 @@ def margin_loss(outputs, ILL, neg_left, neg_right, neg2_left, neg2_right, k, gam
     B1 = (outputs[ix(neg_left)] - outputs[ix(neg_right)]).abs().sum(1).reshape(t, k)
     B2 = (outputs[ix(neg2_left)] - outputs[ix(neg2_right)]).abs().sum(1).reshape(t, k)
     return (F.relu(D - B1).sum() + F.relu(D - B2).sum()) / (2.0 * t * k)
+
+
+# --------------------------------------------------------------------------- #
+# §8f-3  Gromov-Wasserstein by iterative projection                            #
+# --------------------------------------------------------------------------- #
+
+
+def gw_iterative(C1, C2, mu, nu, epsilon, max_iter, tol=1e-9):
+    """SinkhornOT/iterative_projection.py:8-60 with g=False (gw_iterative_1, :119-120) and
+    cderivation.py:147-163,180-183: constC = ½(C1² mu 1ᵀ + 1 nuᵀ C2ᵀ²); L(T) = constC - C1 T C2ᵀ;
+    T <- sinkhorn_stabilised(2 L(T), mu, nu, eps); stop when ||T_old - T||_F < tol.  Returns (T [1,I,J], gw)."""
+    I, J = C1.shape[0], C2.shape[0]
+    mu3, nu3 = mu.reshape(1, I, 1), nu.reshape(1, 1, J)
+    constC = 0.5 * (C1 ** 2) @ mu.reshape(I, 1) + 0.5 * nu.reshape(1, J) @ (C2.t() ** 2)
+    T_old = torch.full((I, J), 1.0 / (I * J), dtype=C1.dtype)
+    lt = constC - C1 @ (T_old @ C2.t())
+    gw = (T_old * lt).sum()
+    T = T_old
+    for _ in range(max_iter):
+        gw, _, _, T = sinkhorn_stabilised(2 * lt.reshape(1, I, J), mu3, nu3, epsilon)
+        if torch.linalg.norm((T_old - T).reshape(-1)) < tol:
+            break
+        T_old = T
+        lt = constC - C1 @ (T_old.reshape(I, J) @ C2.t())
+    return T, gw

@@ -47,6 +47,7 @@ class _RefModules:
         "sinkhorn_loss": "SinkhornOT.sinkhorn_loss",
         "cderivation": "SinkhornOT.cderivation",
         "models_ea": "models.models_ea",
+        "iterative_projection": "SinkhornOT.iterative_projection",
     }
 
     def __getattr__(self, key):

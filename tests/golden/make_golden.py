@@ -165,7 +165,24 @@ def margin_fixture():
              loss=loss.detach().numpy(), grad=out.grad.numpy())
 
 
+def gw_fixture():
+    """gw_iterative_1 of the live reference (SinkhornOT/iterative_projection.py:119-120), fp64, 6 projections."""
+    import contextlib
+    import io
+    rng = np.random.default_rng(8)
+    Va = torch.from_numpy(rng.uniform(size=(18, 6)))
+    Vb = torch.from_numpy(rng.uniform(size=(22, 6)))
+    C1 = ref.cderivation.cos_dist_mat(Va, Va).double()
+    C2 = ref.cderivation.cos_dist_mat(Vb, Vb).double()
+    mu = torch.full((18,), 1 / 18, dtype=torch.float64)
+    nu = torch.full((22,), 1 / 22, dtype=torch.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        T, gw = ref.iterative_projection.gw_iterative_1(C1, C2, mu, nu, epsilon=0.02, max_iter=6)
+    np.savez(os.path.join(HERE, "gw.npz"), C1=C1.numpy(), C2=C2.numpy(), T=T.numpy(), gw=gw.numpy())
+
+
 if __name__ == "__main__":
+    gw_fixture()
     margin_fixture()
     n_ent, KG, adj = adjacency_fixture()
     layer_fixture(n_ent, adj)

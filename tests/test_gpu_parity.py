@@ -421,3 +421,17 @@ def test_margin_loss_golden_and_scale(golden_dir, dev):
     got.backward()
     assert abs(float(got) - float(want)) / float(want) < 1e-5
     assert relerr(xg.grad, xr.grad) < REL
+
+
+def test_gromov_wasserstein_projection_golden(golden_dir, dev):
+    """§8f rank 3: gw_iterative_1 (SinkhornOT/iterative_projection.py:119-120) on the log-domain kernels."""
+    from gnn_mtl_b200.SinkhornOT import gw_iterative_1
+    g = _load(golden_dir, "gw.npz")
+    C1, C2 = torch.from_numpy(g["C1"]).to(dev), torch.from_numpy(g["C2"]).to(dev)
+    mu = torch.full((18,), 1 / 18, dtype=torch.float64, device=dev)
+    nu = torch.full((22,), 1 / 22, dtype=torch.float64, device=dev)
+    T, gw = gw_iterative_1(C1, C2, mu, nu, epsilon=0.02, max_iter=6)
+    assert T.shape == (1, 18, 22)
+    assert relerr(T, g["T"]) < 1e-8 and abs(float(gw) - float(g["gw"])) / abs(float(g["gw"])) < 1e-9
+    T2, log = gw_iterative_1(C1, C2, mu, nu, epsilon=0.02, max_iter=3, log=True)
+    assert len(log["err"]) == 3 and log["gw_dist"] > 0

@@ -119,3 +119,13 @@ def test_margin_loss(golden_dir):
     loss.backward()
     np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
     np.testing.assert_allclose(out.grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
+
+
+def test_gromov_wasserstein_projection(golden_dir):
+    g = _load(golden_dir, "gw.npz")
+    C1, C2 = torch.from_numpy(g["C1"]), torch.from_numpy(g["C2"])
+    mu = torch.full((18,), 1 / 18, dtype=torch.float64)
+    nu = torch.full((22,), 1 / 22, dtype=torch.float64)
+    T, gw = orc.gw_iterative(C1, C2, mu, nu, 0.02, 6)
+    np.testing.assert_allclose(T.numpy(), g["T"], rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(float(gw), float(g["gw"]), rtol=1e-10)
