@@ -19,12 +19,13 @@ namespace eg {
 
 int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
                  const float* pot_in, const float* logw, float* pot_out, float* lse_out, const float* A_hi,
-                 const float* A_lo, const float* B_hi, const float* B_lo, void* ws, size_t ws_bytes,
-                 cudaStream_t s);
+                 const float* A_lo, const float* B_hi, const float* B_lo, const float* A_raw, const float* B_raw,
+                 void* ws, size_t ws_bytes, cudaStream_t s);
 size_t lse_fused_tc_workspace(int64_t nA, int64_t nB, int d);
 int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
                   const float* f, const float* g, double* loss, float* row_sum, const float* A_hi,
-                  const float* A_lo, const float* B_hi, const float* B_lo, cudaStream_t s);
+                  const float* A_lo, const float* B_hi, const float* B_lo, const float* A_raw, const float* B_raw,
+                  cudaStream_t s);
 
 int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_hi, const float* A2_lo, int k2p,
                int64_t m, const float* B_hi, const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1,
@@ -34,12 +35,26 @@ constexpr int kFT = 64;    // tile edge
 constexpr int kFK = 16;    // k-chunk
 constexpr int kFPad = 68;  // [k][i] row stride in floats (272 B: 16-B aligned, skews banks)
 
-__device__ __forceinline__ float cost_from_dot(int cost, float dot, float na, float nb) {
+// Close pairs (squared distance below a quarter of |a|^2 + |b|^2, i.e. cosine > 0.75) are re-evaluated from the
+// rows themselves: the norm expansion cancels catastrophically exactly where the log-sum-exp is decided.
+constexpr float kNearFracSimt = 0.25f;
+__device__ __noinline__ float exact_pair_simt(const float* __restrict__ a, const float* __restrict__ b, int d, int want_dot) {
+  float acc = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const float x = __ldg(a + k), y = __ldg(b + k);
+    acc = want_dot ? fmaf(x, y, acc) : fmaf(x - y, x - y, acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ float cost_from_dot(int cost, float dot, float na, float nb, const float* a_row,
+                                               const float* b_row, int d) {
   if (cost == EG_COST_COSINE) {
     float den = fmaxf(na, 1e-8f) * fmaxf(nb, 1e-8f);
+    if (a_row && dot > (1.f - 2.f * kNearFracSimt) * den) dot = exact_pair_simt(a_row, b_row, d, 1);
     return 1.0f - dot / den;
   }
   float sq = fmaxf(fmaf(-2.0f, dot, na + nb), 0.0f);
+  if (a_row && sq < kNearFracSimt * (na + nb)) sq = exact_pair_simt(a_row, b_row, d, 0);
   return cost == EG_COST_L2 ? sqrtf(sq) : sq;
 }
 
@@ -135,7 +150,9 @@ fused_simt_kernel(int cost, const float* __restrict__ A, int64_t nA, const float
       float z[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        float c = cost_from_dot(cost, acc[a][b], na[a], nb[b]);
+        const int64_t gi = i0 + 4 * ty + a, gj = j0 + 4 * tx + b;
+        const bool live = okb[b] && gi < nA;
+        float c = cost_from_dot(cost, acc[a][b], na[a], nb[b], live ? A + gi * d : nullptr, live ? B + gj * d : nullptr, d);
         if (MODE == 0) {
           z[b] = okb[b] ? fmaf(-c, inv_reg, gb[b]) : -CUDART_INF_F;
         } else {
@@ -277,7 +294,7 @@ int eg_lse_fused(int algo, int cost, const float* A, int64_t nA, const float* B,
   if (algo == EG_ALGO_TCGEN05) {
     if (!A_hi || !A_lo || !B_hi || !B_lo) return EG_ERR_INVALID;
     return lse_fused_tc(cost, nA, nB, d, normA, normB, inv_reg, pot_in, logw, pot_out, lse_out, A_hi, A_lo, B_hi,
-                        B_lo, ws, ws_bytes, s);
+                        B_lo, A, B, ws, ws_bytes, s);
   }
   if (algo != EG_ALGO_SIMT || !A || !B) return EG_ERR_INVALID;
   int splits = pick_splits(nA, nB);
@@ -325,7 +342,7 @@ int eg_plan_fused(int algo, int cost, const float* A, int64_t nA, const float* B
   if (algo == EG_ALGO_TCGEN05) {
     if (P) return EG_ERR_UNSUPPORTED;   // the plan itself is only ever written by the SIMT path (small sizes)
     if (!A_hi || !A_lo || !B_hi || !B_lo) return EG_ERR_INVALID;
-    return plan_fused_tc(cost, nA, nB, d, normA, normB, inv_reg, f, g, loss, row_sum, A_hi, A_lo, B_hi, B_lo, s);
+    return plan_fused_tc(cost, nA, nB, d, normA, normB, inv_reg, f, g, loss, row_sum, A_hi, A_lo, B_hi, B_lo, A, B, s);
   }
   if (algo != EG_ALGO_SIMT || !A || !B) return EG_ERR_INVALID;
   int splits = pick_splits(nA, nB);

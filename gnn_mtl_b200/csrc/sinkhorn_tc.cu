@@ -106,6 +106,36 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// |a|^2 + |b|^2 - 2 a.b cancels catastrophically for close pairs (the pairs that dominate the log-sum-exp of an
+// alignment problem), turning the ~2e-6 relative error of the 3xTF32 dot into 1e-3 of the cost.  Pairs whose
+// squared distance comes out below a quarter of |a|^2 + |b|^2 (cosine > 0.75) are re-evaluated from the fp32
+// rows: sum (a_k - b_k)^2, or the exact dot for the cosine cost.  Rare by construction, so the cost is noise.
+constexpr float kNearFrac = 0.25f;
+// All 32 lanes evaluate ONE pair together: coalesced 16-byte loads of both rows, shuffle reduction.
+__device__ __forceinline__ float exact_pair_warp(const float* __restrict__ a, const float* __restrict__ b, int d,
+                                                 int want_dot, int lane) {
+  float acc = 0.f;
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (int k = lane; k < d / 4; k += 32) {
+      const float4 x = __ldg(a4 + k), y = __ldg(b4 + k);
+      if (want_dot) {
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+      } else {
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+      }
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      const float x = __ldg(a + k), y = __ldg(b + k);
+      acc = want_dot ? fmaf(x, y, acc) : fmaf(x - y, x - y, acc);
+    }
+  }
+  return warp_sum(acc);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -137,6 +167,9 @@ struct Params {
   const float* pot_a;      // f_i                                 (MODE 1)
   double* loss;            // sum_ij P_ij * cost_ij               (MODE 1)
   float* row_sum;          // sum_j P_ij, atomically accumulated  (MODE 1, nullable)
+  const float* A_raw;      // fp32 rows [nA, d] / [nB, d]: close pairs are re-evaluated exactly from these (MODE 0/1)
+  const float* B_raw;
+  int d;
   int kb_split;            // k-blocks taken from the first A operand; the rest come from A2 (MODE 2: A = [A1 | A2])
   float* out1;             // C[:, 0:n1)   row stride ld1          (MODE 2)
   float* out2;             // C[:, n1:nB)  row stride ld2          (MODE 2, nullable)
@@ -251,6 +284,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int64_t row = i0 + row_in_tile;
     const float na = (MODE != 2 && row < p.nA) ? p.normA[row] : 0.f;
     const float fa = (MODE == 1 && row < p.nA) ? p.pot_a[row] : -CUDART_INF_F;
+    const bool near_ok = (MODE != 2) && row < p.nA && p.A_raw != nullptr && p.B_raw != nullptr;
     float run_m = -CUDART_INF_F, run_s = 0.f;
     double loss_acc = 0.0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -290,23 +324,66 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         float z[32];
         float zmax = -CUDART_INF_F;
+        float near_min = 1.f;        // < 0 iff some pair of this chunk needs the exact re-evaluation
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const float4 info = *reinterpret_cast<const float4*>(&ci[c0 + c]);   // (nb0, pot0, nb1, pot1)
           float cst0, cst1;
           if (p.cost == EG_COST_COSINE) {
-            cst0 = 1.0f - __fdividef(dot[c], fmaxf(na, 1e-8f) * fmaxf(info.x, 1e-8f));
-            cst1 = 1.0f - __fdividef(dot[c + 1], fmaxf(na, 1e-8f) * fmaxf(info.z, 1e-8f));
+            const float den0 = fmaxf(na, 1e-8f) * fmaxf(info.x, 1e-8f), den1 = fmaxf(na, 1e-8f) * fmaxf(info.z, 1e-8f);
+            near_min = fminf(near_min, fminf(fmaf(1.f - 2.f * kNearFrac, den0, -dot[c]),
+                                             fmaf(1.f - 2.f * kNearFrac, den1, -dot[c + 1])));
+            cst0 = 1.0f - __fdividef(dot[c], den0);
+            cst1 = 1.0f - __fdividef(dot[c + 1], den1);
           } else {
-            float sq0 = fmaxf(fmaf(-2.0f, dot[c], na + info.x), 0.f);
-            float sq1 = fmaxf(fmaf(-2.0f, dot[c + 1], na + info.z), 0.f);
-            cst0 = (p.cost == EG_COST_L2) ? fast_sqrt(sq0) : sq0;
-            cst1 = (p.cost == EG_COST_L2) ? fast_sqrt(sq1) : sq1;
+            const float s0 = na + info.x, s1 = na + info.z;
+            const float sq0 = fmaf(-2.0f, dot[c], s0), sq1 = fmaf(-2.0f, dot[c + 1], s1);
+            near_min = fminf(near_min, fminf(fmaf(-kNearFrac, s0, sq0), fmaf(-kNearFrac, s1, sq1)));
+            cst0 = (p.cost == EG_COST_L2) ? fast_sqrt(fmaxf(sq0, 0.f)) : fmaxf(sq0, 0.f);
+            cst1 = (p.cost == EG_COST_L2) ? fast_sqrt(fmaxf(sq1, 0.f)) : fmaxf(sq1, 0.f);
           }
           z[c] = fmaf(-cst0, p.inv_reg, info.y);       // pot = -inf on padded columns -> z = -inf
           z[c + 1] = fmaf(-cst1, p.inv_reg, info.w);
-          zmax = fmaxf(zmax, fmaxf(z[c], z[c + 1]));
         }
+        // rare and warp-uniform: lanes that found close pairs in this chunk take turns; for each such pair the
+        // WHOLE warp re-evaluates it from the fp32 rows (exact_pair_warp) and the owner patches its z
+        unsigned owners = (MODE != 2) ? __ballot_sync(0xffffffffu, near_ok && near_min < 0.f) : 0u;
+        while (owners) {
+          const int src = __ffs(owners) - 1;
+          owners &= owners - 1;
+          unsigned mine = 0;
+          if (lane == src) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float2 inf2 = ci[c0 + c];
+              bool hit;
+              if (p.cost == EG_COST_COSINE)
+                hit = dot[c] > (1.f - 2.f * kNearFrac) * fmaxf(na, 1e-8f) * fmaxf(inf2.x, 1e-8f);
+              else
+                hit = fmaf(-2.0f, dot[c], na + inf2.x) < kNearFrac * (na + inf2.x);
+              if (hit && inf2.y > -CUDART_INF_F) mine |= 1u << c;
+            }
+          }
+          unsigned cols = __shfl_sync(0xffffffffu, mine, src);
+          const float* arow = p.A_raw + (i0 + quad * 32 + src) * p.d;
+          while (cols) {
+            const int c = __ffs(cols) - 1;
+            cols &= cols - 1;
+            const float ex = exact_pair_warp(arow, p.B_raw + (j0 + c0 + c) * p.d, p.d, p.cost == EG_COST_COSINE, lane);
+            if (lane == src) {
+              const float2 inf2 = ci[c0 + c];
+              float cst;
+              if (p.cost == EG_COST_COSINE) cst = 1.0f - __fdividef(ex, fmaxf(na, 1e-8f) * fmaxf(inf2.x, 1e-8f));
+              else cst = (p.cost == EG_COST_L2) ? fast_sqrt(ex) : ex;
+              const float znew = fmaf(-cst, p.inv_reg, inf2.y);
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc)
+                if (cc == c) z[cc] = znew;
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) zmax = fmaxf(zmax, z[c]);
         if (MODE == 0) {
           if (zmax > run_m) { run_s *= __expf(run_m - zmax); run_m = zmax; }
           if (run_m > -CUDART_INF_F) {
@@ -445,7 +522,7 @@ struct Launch {
 };
 static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB,
                    float inv_reg, const float* pot_in, const float* A_hi, const float* A_lo, const float* B_hi,
-                   const float* B_lo) {
+                   const float* B_lo, const float* A_raw, const float* B_raw) {
   // operands come from eg_split_tf32: [n, d_pad] with d_pad = d rounded up to 8; the k-loop runs over whole
   // BK-element blocks and relies on TMA zero fill past d_pad
   const int d_pad = (d + 7) / 8 * 8;
@@ -462,6 +539,7 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
   p = Params{};
   p.nA = nA; p.nB = nB; p.k_blocks = (d_pad + BK - 1) / BK; p.d_pad = d_pad; p.cost = cost; p.inv_reg = inv_reg;
   p.normA = normA; p.normB = normB; p.pot_in = pot_in;
+  p.A_raw = A_raw; p.B_raw = B_raw; p.d = d;
   pick_grid(nA, nB, &L->splits, &p.tiles_per_split);
   static bool attr_set = false;
   if (!attr_set) {
@@ -476,11 +554,11 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
 
 int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
                  const float* pot_in, const float* logw, float* pot_out, float* lse_out, const float* A_hi,
-                 const float* A_lo, const float* B_hi, const float* B_lo, void* ws, size_t ws_bytes,
-                 cudaStream_t s) {
+                 const float* A_lo, const float* B_hi, const float* B_lo, const float* A_raw, const float* B_raw,
+                 void* ws, size_t ws_bytes, cudaStream_t s) {
   using namespace tc;
   Launch L;
-  int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, pot_in, A_hi, A_lo, B_hi, B_lo);
+  int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, pot_in, A_hi, A_lo, B_hi, B_lo, A_raw, B_raw);
   if (rc) return rc;
   size_t half = align_up(sizeof(float) * (size_t)L.splits * (size_t)nA);
   if (ws_bytes < 2 * half) return EG_ERR_WORKSPACE;
@@ -498,10 +576,11 @@ int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, co
 // Plan statistics on the same tiles: *loss = sum P∘cost, row_sum[i] = sum_j P_ij (both pre-zeroed by the caller).
 int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB, float inv_reg,
                   const float* f, const float* g, double* loss, float* row_sum, const float* A_hi,
-                  const float* A_lo, const float* B_hi, const float* B_lo, cudaStream_t s) {
+                  const float* A_lo, const float* B_hi, const float* B_lo, const float* A_raw, const float* B_raw,
+                  cudaStream_t s) {
   using namespace tc;
   Launch L;
-  int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, g, A_hi, A_lo, B_hi, B_lo);
+  int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, g, A_hi, A_lo, B_hi, B_lo, A_raw, B_raw);
   if (rc) return rc;
   L.p.pot_a = f; L.p.loss = loss; L.p.row_sum = row_sum;
   dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);

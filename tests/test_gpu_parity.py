@@ -435,3 +435,30 @@ def test_gromov_wasserstein_projection_golden(golden_dir, dev):
     assert relerr(T, g["T"]) < 1e-8 and abs(float(gw) - float(g["gw"])) / abs(float(g["gw"])) < 1e-9
     T2, log = gw_iterative_1(C1, C2, mu, nu, epsilon=0.02, max_iter=3, log=True)
     assert len(log["err"]) == 3 and log["gw_dist"] > 0
+
+
+@pytest.mark.parametrize("algo", ["simt", "tcgen05"])
+@pytest.mark.parametrize("cost", ["l2", "sqeuclid", "cos"])
+def test_fused_lse_close_pairs(cost, algo, dev):
+    """Aligned entities are CLOSE pairs: |a|²+|b|²-2a·b cancels there and would turn the 3xTF32 dot error into
+    1e-3 of the cost; the kernels re-evaluate such pairs from the fp32 rows.  Checked against fp64."""
+    from gnn_mtl_b200 import _lib, ops
+    torch.manual_seed(5)
+    n, d = 3000, 300
+    X = torch.randn(n, d, device=dev) / d ** 0.5
+    Y = X[torch.randperm(n, device=dev)] + 0.05 * torch.randn(n, d, device=dev) / d ** 0.5
+    Y[:10] = X[:10]                                            # exact duplicates too
+    cid = {"l2": _lib.COST_L2, "sqeuclid": _lib.COST_SQEUCLID, "cos": _lib.COST_COSINE}[cost]
+    aid = {"simt": _lib.ALGO_SIMT, "tcgen05": _lib.ALGO_TCGEN05}[algo]
+    A, B = ops.FusedOperand(X, cid, aid), ops.FusedOperand(Y, cid, aid)
+    pot = torch.randn(n, device=dev)
+    inv = 20.0 if cost == "l2" else 100.0
+    _, got = ops.lse_fused(A, B, cid, inv, pot, None, aid, want_pot=False, want_lse=True)
+    Xd, Yd = X.double(), Y.double()
+    if cost == "cos":
+        C = 1 - (Xd / Xd.norm(dim=1, keepdim=True)) @ (Yd / Yd.norm(dim=1, keepdim=True)).t()
+    else:
+        C = torch.cdist(Xd, Yd)
+        C = C * C if cost == "sqeuclid" else C
+    ref = torch.logsumexp(pot.double()[None, :] - C * inv, 1)
+    assert float((got.double() - ref).abs().max()) < 3e-5
