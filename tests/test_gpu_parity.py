@@ -461,4 +461,5 @@ def test_fused_lse_close_pairs(cost, algo, dev):
         C = torch.cdist(Xd, Yd)
         C = C * C if cost == "sqeuclid" else C
     ref = torch.logsumexp(pot.double()[None, :] - C * inv, 1)
-    assert float((got.double() - ref).abs().max()) < 3e-5
+    # the exponent is cost*inv: a cost evaluated in fp32 carries ~1e-6 absolute error, amplified by inv
+    assert float((got.double() - ref).abs().max()) < max(3e-5, 1.5e-6 * inv)
