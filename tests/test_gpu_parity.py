@@ -463,3 +463,21 @@ def test_fused_lse_close_pairs(cost, algo, dev):
     ref = torch.logsumexp(pot.double()[None, :] - C * inv, 1)
     # the exponent is cost*inv: a cost evaluated in fp32 carries ~1e-6 absolute error, amplified by inv
     assert float((got.double() - ref).abs().max()) < max(3e-5, 1.5e-6 * inv)
+
+
+def test_one_graph_adjacency_with_id_remap(dev):
+    """get_sparse_tensor_for_one_graph (utils/data_utils.py:339-350): ids remapped through index_R."""
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200.utils.data_utils import get_sparse_tensor_for_one_graph, sparse_mx_to_torch_sparse_tensor
+    rng = np.random.default_rng(2)
+    ids = rng.permutation(5000)[:300] + 100          # arbitrary global ids of one KG
+    index_R = {int(v): i for i, v in enumerate(ids)}
+    KG = [(int(ids[a]), int(r), int(ids[b])) for a, r, b in zip(rng.integers(0, 300, 900), rng.integers(0, 9, 900),
+                                                               rng.integers(0, 300, 900))]
+    adj = get_sparse_tensor_for_one_graph(300, KG, index_R, device=dev)
+    h = np.array([index_R[t[0]] for t in KG]); t = np.array([index_R[t[2]] for t in KG])
+    crow, col, val = orc.adjacency_csr(300, h, t)
+    assert np.array_equal(adj.crow.cpu().numpy(), crow) and np.array_equal(adj.col64.cpu().numpy(), col)
+    assert np.array_equal(adj.val.cpu().numpy().view(np.uint32), val.view(np.uint32))
+    coo = sparse_mx_to_torch_sparse_tensor(adj)
+    assert coo.is_sparse and coo.is_cuda and coo.shape == (300, 300) and coo._nnz() == len(col)
