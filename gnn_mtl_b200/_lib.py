@@ -33,7 +33,7 @@ SIGNATURES = {
     "eg_adj_workspace_bytes": (_sz, [_i64, _i64]),
     "eg_adj_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "eg_csr_transpose_workspace_bytes": (_sz, [_i64, _i64, _i64]),
-    "eg_csr_transpose": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "eg_csr_transpose": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "eg_spmm": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32,
                           _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "eg_epilogue_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
@@ -59,6 +59,9 @@ SIGNATURES = {
                                     _i64, _vp]),
     "eg_margin_loss_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp]),
     "eg_margin_loss_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),
+    "eg_gat_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "eg_gat_bwd_edges": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eg_permute_edges": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 
 

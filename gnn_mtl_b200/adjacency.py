@@ -155,9 +155,12 @@ class DeviceAdjacency:
                 rp = torch.empty(c.n_cols + 1, dtype=torch.int32, device=dev)
                 ct = torch.empty(max(c.nnz, 1), dtype=torch.int32, device=dev)[:c.nnz]
                 vt = torch.empty(max(c.nnz, 1), dtype=torch.float32, device=dev)[:c.nnz]
+                pt = torch.empty(max(c.nnz, 1), dtype=torch.int32, device=dev)[:c.nnz]
                 check(lib.eg_csr_transpose(c.n_rows, c.n_cols, c.nnz, ptr(c.rowptr), ptr(c.col), ptr(c.val), ptr(ws),
-                                           ws.numel(), ptr(rp), ptr(ct), ptr(vt), stream()), "eg_csr_transpose")
+                                           ws.numel(), ptr(rp), ptr(ct), ptr(vt), ptr(pt), stream()),
+                      "eg_csr_transpose")
             self._csr_t = _Csr(c.n_cols, c.n_rows, rp, ct, vt)
+            self._csr_t.perm = pt        # position in CSR(A) of every entry of CSR(Aᵀ)
         return self._csr_t
 
     def to_torch_coo(self):

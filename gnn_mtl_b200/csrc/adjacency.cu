@@ -134,11 +134,13 @@ __global__ void transpose_keys_kernel(const int32_t* __restrict__ rowptr, const 
 
 __global__ void transpose_emit_kernel(const unsigned long long* __restrict__ keys,
                                       const int32_t* __restrict__ pos, const float* __restrict__ val,
-                                      int64_t nnz, int32_t* __restrict__ col_t, float* __restrict__ val_t) {
+                                      int64_t nnz, int32_t* __restrict__ col_t, float* __restrict__ val_t,
+                                      int32_t* __restrict__ perm_t) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nnz) return;
   col_t[i] = (int32_t)(keys[i] & 0xffffffffull);
   val_t[i] = val[pos[i]];
+  if (perm_t) perm_t[i] = pos[i];
 }
 
 struct TrWorkspace {
@@ -223,7 +225,7 @@ size_t eg_csr_transpose_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_c
 
 int eg_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr, const int32_t* col,
                      const float* val, void* ws, size_t ws_bytes, int32_t* rowptr_t, int32_t* col_t,
-                     float* val_t, eg_stream_t stream_) {
+                     float* val_t, int32_t* perm_t, eg_stream_t stream_) {
   using namespace eg;
   if (n_rows < 0 || n_cols <= 0 || nnz < 0 || !rowptr || !rowptr_t || !ws) return EG_ERR_INVALID;
   if (nnz > 0 && (!col || !val || !col_t || !val_t)) return EG_ERR_INVALID;
@@ -241,7 +243,7 @@ int eg_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t*
     EG_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tmp, w.keys_a, w.keys_b, w.pos_a, w.pos_b, nnz, 0, 64, s));
     g_launches.fetch_add(1);
     sorted = w.keys_b;
-    transpose_emit_kernel<<<(unsigned)ceil_div(nnz, T), T, 0, s>>>(w.keys_b, w.pos_b, val, nnz, col_t, val_t);
+    transpose_emit_kernel<<<(unsigned)ceil_div(nnz, T), T, 0, s>>>(w.keys_b, w.pos_b, val, nnz, col_t, val_t, perm_t);
     EG_LAUNCHED();
   }
   rowptr_from_keys_kernel<<<(unsigned)ceil_div(n_cols + 1, T), T, 0, s>>>(sorted, w.nnz_dev, n_cols, nullptr, rowptr_t);

@@ -2,6 +2,7 @@
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..layers.att_layers import GraphAttentionLayer
 from ..layers.layers import GraphConvolution, HighWayGraphConvolution, Linear
 
 
@@ -27,6 +28,14 @@ class GCNDecoder(Decoder):
         self.cls = GraphConvolution(args.dim, args.n_classes, args.dropout, _identity, args.bias)
 
 
+class GATDecoder(Decoder):
+    """One single-head ELU attention layer (models/decoders.py:31-37)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.cls = GraphAttentionLayer(args.dim, args.n_classes, args.dropout, F.elu, args.alpha, 1, True)
+
+
 class HGCNDecoder(Decoder):
     """One identity-activation highway layer (models/decoders.py:40-47)."""
 
@@ -49,4 +58,4 @@ class MLPDecoder(Decoder):
                                    for i in range(3)])
 
 
-model2decoder = {'GCN': MLPDecoder, 'HGCN': HGCNDecoder, 'Distill': HGCNDecoder}
+model2decoder = {'GCN': MLPDecoder, 'GAT': MLPDecoder, 'HGCN': HGCNDecoder, 'Distill': HGCNDecoder}

@@ -1,7 +1,8 @@
 """Graph encoders: the reference's models/encoders.py wiring (:6-94) over the
-eagraft layers.  GAT is out of scope."""
+eagraft layers."""
 import torch.nn as nn
 
+from ..layers.att_layers import GraphAttentionLayer
 from ..layers.layers import GraphConvolution, HighWayGraphConvolution, Linear, get_dim_act
 
 
@@ -36,6 +37,21 @@ class GCN(Encoder):
         self._stack(args, lambda i, o, a: GraphConvolution(i, o, args.dropout, a, args.bias))
 
 
+class GAT(Encoder):
+    """Graph attention encoder (models/encoders.py:69-86): n_heads heads of width dim / n_heads, concatenated."""
+
+    def __init__(self, args):
+        super().__init__()
+        assert args.num_layers > 0
+        dims, acts = get_dim_act(args)
+        gat_layers = []
+        for i in range(len(dims) - 1):
+            assert dims[i + 1] % args.n_heads == 0
+            gat_layers.append(GraphAttentionLayer(dims[i], dims[i + 1] // args.n_heads, args.dropout, acts[i],
+                                                  args.alpha, args.n_heads, True))
+        self.layers = nn.Sequential(*gat_layers)
+
+
 class HGCN(Encoder):
     def __init__(self, args):
         super().__init__()
@@ -43,4 +59,4 @@ class HGCN(Encoder):
                                                                    args.cuda, args.device))
 
 
-model2encoder = {'GCN': GCN, 'HGCN': HGCN, 'Distill': HGCN, 'MLP': MLP}
+model2encoder = {'GCN': GCN, 'GAT': GAT, 'HGCN': HGCN, 'Distill': HGCN, 'MLP': MLP}

@@ -385,3 +385,60 @@ def margin_loss(outputs, left, right, nl, nr, n2l, n2r, k, gamma=1.0):
         a = a if torch.is_tensor(a) else torch.as_tensor(a)
         return a.to(device=dev, dtype=torch.int64).contiguous()
     return _MarginLoss.apply(outputs, ix(left), ix(right), ix(nl), ix(nr), ix(n2l), ix(n2r), k, gamma)
+
+
+# ---- GAT edge-softmax aggregation (layers/att_layers.py:29-61) ------------------------------------
+
+class _GatAggregate(torch.autograd.Function):
+    """y_i = (sum_j m_ij w_ij h_j) / sum_j w_ij, w_ij = exp(-leakyrelu(s1_i + s2_j)) over the edges of A."""
+
+    @staticmethod
+    def forward(ctx, h, s1, s2, adjacency, alpha, edge_scale):
+        c = adjacency.csr
+        h, s1, s2 = _f32c(h), _f32c(s1), _f32c(s2)
+        if h.shape[0] != c.n_cols or s1.numel() != c.n_rows or s2.numel() != c.n_cols:
+            raise ValueError("gat_aggregate: h/s1/s2 do not match the adjacency shape")
+        y = torch.empty(c.n_rows, h.shape[1], dtype=torch.float32, device=h.device)
+        wsum = torch.empty(c.n_rows, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            check(lib.eg_gat_fwd(ptr(c.rowptr), ptr(c.col), c.n_rows, ptr(h), h.shape[1], ptr(s1), ptr(s2),
+                                 float(alpha), ptr(edge_scale), ptr(y), ptr(wsum), stream()), "eg_gat_fwd")
+        ctx.save_for_backward(h, s1, s2, y, wsum)
+        ctx.adjacency, ctx.alpha, ctx.edge_scale = adjacency, float(alpha), edge_scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, s1, s2, y, wsum = ctx.saved_tensors
+        adjacency = ctx.adjacency
+        c, ct = adjacency.csr, adjacency.csr_t
+        dy = _f32c(dy)
+        dev = h.device
+        p_edge = torch.empty(max(c.nnz, 1), dtype=torch.float32, device=dev)
+        p_t = torch.empty_like(p_edge)
+        ds1 = torch.empty_like(s1)
+        ds2 = torch.empty_like(s2)
+        with torch.cuda.device(dev):
+            check(lib.eg_gat_bwd_edges(ptr(c.rowptr), ptr(c.col), c.n_rows, c.n_cols, ptr(h), h.shape[1], ptr(s1),
+                                       ptr(s2), ctx.alpha, ptr(ctx.edge_scale), ptr(y), ptr(wsum), ptr(dy),
+                                       ptr(p_edge), ptr(ds1), ptr(ds2), stream()), "eg_gat_bwd_edges")
+            check(lib.eg_permute_edges(ptr(p_edge), ptr(ct.perm), c.nnz, ptr(p_t), stream()), "eg_permute_edges")
+            dh = torch.empty_like(h)
+            scratch = ct.scratch(h.shape[1])
+            check(lib.eg_spmm(ptr(ct.rowptr), ptr(ct.col), ptr(p_t), ct.n_rows, ptr(dy), h.shape[1],
+                              _lib.ACT_IDENTITY, None, None, ptr(dh), None, ct.threshold, ptr(ct.seg_row),
+                              ptr(ct.seg_begin), ptr(ct.seg_end), ct.n_seg, ptr(ct.long_rows), ptr(ct.long_first),
+                              ct.n_long, ptr(scratch), stream()), "eg_spmm")
+        return dh, ds1, ds2, None, None, None
+
+
+def gat_aggregate(h, s1, s2, adjacency, alpha, edge_scale=None):
+    """Differentiable (h, s1, s2) -> y; ``adjacency`` is a DeviceAdjacency (only its structure is used)."""
+    _lib.require_cuda(h, s1, s2, edge_scale)
+    if getattr(adjacency, "sharded", False):
+        raise NotImplementedError("gat_aggregate: row-sharded adjacencies are not supported")
+    if edge_scale is not None:
+        edge_scale = _f32c(edge_scale)
+        if edge_scale.numel() != adjacency.csr.nnz:
+            raise ValueError("gat_aggregate: edge_scale must have one entry per stored edge")
+    return _GatAggregate.apply(h, s1.reshape(-1), s2.reshape(-1), adjacency, alpha, edge_scale)

@@ -66,13 +66,14 @@ int eg_adj_build(const int64_t* heads, const int64_t* tails, int64_t n_triples, 
                  int64_t* h_nnz /* host */, eg_stream_t stream);
 
 /* CSR -> CSR of the transpose (for dH = A^T dS; layers/layers.py:35,64 autograd).
- * Entries of each output row are ordered by ascending source row. */
+ * Entries of each output row are ordered by ascending source row.  perm_t (nullable, [nnz]) receives,
+ * for every transposed entry, its position in the source CSR (to carry per-edge values across). */
 size_t eg_csr_transpose_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);
 int eg_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz,
                      const int32_t* rowptr, const int32_t* col, const float* val,
                      void* ws, size_t ws_bytes,
                      int32_t* rowptr_t /* [n_cols+1] */, int32_t* col_t /* [nnz] */, float* val_t /* [nnz] */,
-                     eg_stream_t stream);
+                     int32_t* perm_t /* [nnz], nullable */, eg_stream_t stream);
 
 /* ---- (a) message-passing SpMM with fused epilogue ----------------------------
  * Replaces torch.spmm(adj, hidden) + act + highway blend, layers/layers.py:35-38
@@ -213,6 +214,23 @@ int eg_margin_loss_fwd(const float* out, int64_t n, int d, const int64_t* left, 
 int eg_margin_loss_bwd(const float* out, int64_t n, int d, const int64_t* left, const int64_t* right,
                        const int64_t* nl, const int64_t* nr, const int64_t* n2l, const int64_t* n2r,
                        int64_t t, int k, float gamma, float scale, float* grad, eg_stream_t stream);
+
+/* ---- GAT edge-softmax aggregation (layers/att_layers.py:29-61) ----------
+ *   w_ij = exp(-leakyrelu_alpha(s1_i + s2_j)) over the stored (i, j) of A (values of A unused),
+ *   W_i = sum_j w_ij (-> wsum, nullable),  out_i = (sum_j m_ij w_ij h_j) / W_i   (pre-activation)
+ * m = edge_scale (nullable, [nnz] in CSR order): the edge-dropout mask/scale the reference applies AFTER the
+ * row sum (:50).
+ * eg_gat_bwd_edges: from dy = dL/d out it writes p_edge[e] = m_ij w_ij / W_i (CSR edge order), ds1 [n_rows] and
+ * ds2 [n_cols] (zeroed by the call, accumulated atomically); dh = P^T dy is then an ordinary eg_spmm over
+ * CSR(A^T) whose values are p_edge permuted with eg_permute_edges(p_edge, perm_t).  d <= 512. */
+int eg_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* h, int d,
+               const float* s1, const float* s2, float alpha, const float* edge_scale,
+               float* out, float* wsum, eg_stream_t stream);
+int eg_gat_bwd_edges(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols,
+                     const float* h, int d, const float* s1, const float* s2, float alpha,
+                     const float* edge_scale, const float* y, const float* wsum, const float* dy,
+                     float* p_edge, float* ds1, float* ds2, eg_stream_t stream);
+int eg_permute_edges(const float* src, const int32_t* perm, int64_t n, float* dst, eg_stream_t stream);
 
 #ifdef __cplusplus
 }

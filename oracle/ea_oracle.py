@@ -146,6 +146,28 @@ def hgcn_stack(x, adj, params, acts):
     return h
 
 
+def gat_layer(x, adj, W, a, alpha=0.2, act="identity"):
+    """layers/att_layers.py:29-61 (dropout p=0): sparse single-head graph attention.
+
+    h = x W;  e_ij = exp(-leakyrelu_alpha(a · [h_i ‖ h_j])) on the stored (i, j) of adj (its values are not used);
+    out = act((sum_j e_ij h_j) / sum_j e_ij).  Differentiable torch ops in the input dtype.
+    """
+    edge = adj.coalesce().indices()
+    h = x @ W
+    edge_h = torch.cat((h[edge[0]], h[edge[1]]), dim=1)                 # [E, 2D]
+    edge_e = torch.exp(-F.leaky_relu(edge_h @ a.reshape(-1), alpha))    # [E]
+    n = x.shape[0]
+    rowsum = torch.zeros(n, dtype=h.dtype).index_add(0, edge[0], edge_e)
+    agg = torch.zeros(n, h.shape[1], dtype=h.dtype).index_add(0, edge[0], edge_e[:, None] * h[edge[1]])
+    return _act(act)(agg / rowsum[:, None])
+
+
+def gat_multihead(x, adj, heads, alpha=0.2, act="identity", concat=True):
+    """layers/att_layers.py:81-93: ``heads`` = list of (W, a); concatenate or average the head outputs."""
+    outs = [gat_layer(x, adj, W, a, alpha, act) for W, a in heads]
+    return torch.cat(outs, dim=1) if concat else torch.stack(outs, dim=2).mean(dim=2)
+
+
 # --------------------------------------------------------------------------- #
 # S4  cost matrices                                                           #
 # --------------------------------------------------------------------------- #

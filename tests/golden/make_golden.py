@@ -181,7 +181,46 @@ def gw_fixture():
     np.savez(os.path.join(HERE, "gw.npz"), C1=C1.numpy(), C2=C2.numpy(), T=T.numpy(), gw=gw.numpy())
 
 
+def gat_fixture():
+    """SpGraphAttentionLayer / GraphAttentionLayer (layers/att_layers.py) on a graph with no isolated entity
+    (the reference asserts on the NaN an empty row would give)."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(23)
+    n_ent = 48
+    KG = tiny_triples(rng, n_ent, 150, 5) + [(i, 0, i + 1) for i in range(n_ent - 1)]
+    adj = ref.data_utils.sparse_mx_to_torch_sparse_tensor(ref.data_utils.get_sparse_tensor(n_ent, KG))
+    att = load_att()
+    torch.manual_seed(9)
+    x = torch.randn(n_ent, 24)
+    out = {"n_ent": n_ent, "triples": np.array(KG, dtype=np.int64), "x": x.numpy()}
+    single = att.SpGraphAttentionLayer(24, 15, 0.0, 0.2, F.elu)
+    xin = x.clone().requires_grad_(True)
+    y = single(xin, adj)
+    seed = torch.randn_like(y)
+    (y * seed).sum().backward()
+    out.update(s_W=single.W.detach().numpy(), s_a=single.a.detach().numpy(), s_y=y.detach().numpy(),
+               s_seed=seed.numpy(), s_dx=xin.grad.numpy(), s_dW=single.W.grad.numpy(), s_da=single.a.grad.numpy())
+    multi = att.GraphAttentionLayer(24, 9, 0.0, F.relu, 0.2, 4, True)
+    xin = x.clone().requires_grad_(True)
+    y, _ = multi((xin, adj))
+    seed = torch.randn_like(y)
+    (y * seed).sum().backward()
+    out.update(m_y=y.detach().numpy(), m_seed=seed.numpy(), m_dx=xin.grad.numpy())
+    for i, head in enumerate(multi.attentions):
+        out["m_W%d" % i] = head.W.detach().numpy()
+        out["m_a%d" % i] = head.a.detach().numpy()
+        out["m_dW%d" % i] = head.W.grad.numpy()
+        out["m_da%d" % i] = head.a.grad.numpy()
+    np.savez(os.path.join(HERE, "gat.npz"), **out)
+
+
+def load_att():
+    from oracle.ref_shim import load
+    return load("layers.att_layers")
+
+
 if __name__ == "__main__":
+    gat_fixture()
     gw_fixture()
     margin_fixture()
     n_ent, KG, adj = adjacency_fixture()

@@ -481,3 +481,118 @@ def test_one_graph_adjacency_with_id_remap(dev):
     assert np.array_equal(adj.val.cpu().numpy().view(np.uint32), val.view(np.uint32))
     coo = sparse_mx_to_torch_sparse_tensor(adj)
     assert coo.is_sparse and coo.is_cuda and coo.shape == (300, 300) and coo._nnz() == len(col)
+
+
+# ------------------------------------------------------------------ GAT (§8f rank 4) --
+
+def test_gat_layers_golden(golden_dir, dev):
+    """SpGraphAttentionLayer / GraphAttentionLayer against the live-reference fixture (outputs + all grads)."""
+    from gnn_mtl_b200.adjacency import DeviceAdjacency
+    from gnn_mtl_b200.layers.att_layers import GraphAttentionLayer, SpGraphAttentionLayer
+    g = _load(golden_dir, "gat.npz")
+    adj = DeviceAdjacency.from_triples(int(g["n_ent"]), g["triples"], device=dev).to_torch_coo()
+    single = SpGraphAttentionLayer(24, 15, 0.0, 0.2, F.elu).to(dev)
+    with torch.no_grad():
+        single.W.copy_(torch.from_numpy(g["s_W"]))
+        single.a.copy_(torch.from_numpy(g["s_a"]))
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    y = single(x, adj)
+    (y * torch.from_numpy(g["s_seed"]).to(dev)).sum().backward()
+    assert relerr(y, g["s_y"]) < REL
+    assert relerr(x.grad, g["s_dx"]) < REL
+    assert relerr(single.W.grad, g["s_dW"]) < REL
+    assert relerr(single.a.grad, g["s_da"]) < REL
+    multi = GraphAttentionLayer(24, 9, 0.0, F.relu, 0.2, 4, True).to(dev)
+    with torch.no_grad():
+        for i, head in enumerate(multi.attentions):
+            head.W.copy_(torch.from_numpy(g["m_W%d" % i]))
+            head.a.copy_(torch.from_numpy(g["m_a%d" % i]))
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    y, adj_out = multi((x, adj))
+    assert adj_out is adj
+    (y * torch.from_numpy(g["m_seed"]).to(dev)).sum().backward()
+    assert relerr(y, g["m_y"]) < REL
+    assert relerr(x.grad, g["m_dx"]) < REL
+    for i, head in enumerate(multi.attentions):
+        assert relerr(head.W.grad, g["m_dW%d" % i]) < REL
+        assert relerr(head.a.grad, g["m_da%d" % i]) < REL
+
+
+@pytest.mark.parametrize("n,d,alpha", [(700, 75, 0.2), (3000, 300, 0.2), (500, 7, 0.01), (400, 512, 0.3)])
+def test_gat_aggregate_vs_oracle_fp64(n, d, alpha, dev):
+    """Kernel-level check on a power-law graph with hub rows: forward, dh, ds1, ds2 against the fp64 oracle,
+    with and without an edge-dropout scale."""
+    from gnn_mtl_b200 import ops, synth
+    from gnn_mtl_b200.adjacency import DeviceAdjacency
+    from oracle import ea_oracle as orc
+    heads, tails = synth.make_powerlaw_graph(n, 12, seed=n + d)
+    chain = np.arange(n - 1)
+    heads, tails = np.concatenate([heads, chain]), np.concatenate([tails, chain + 1])   # no isolated entity
+    A = DeviceAdjacency.from_heads_tails(n, torch.from_numpy(heads).to(dev), torch.from_numpy(tails).to(dev))
+    adj_cpu = orc.adjacency_torch_coo(n, heads, tails)
+    gen = torch.Generator().manual_seed(3)
+    h = torch.randn(n, d, generator=gen, dtype=torch.float64)
+    a = torch.randn(1, 2 * d, generator=gen, dtype=torch.float64) / d ** 0.5
+    seed = torch.randn(n, d, generator=gen, dtype=torch.float64)
+    # oracle with W = I so the aggregation alone is exercised
+    h64 = h.clone().requires_grad_(True)
+    a64 = a.clone().requires_grad_(True)
+    y64 = orc.gat_layer(h64, adj_cpu, torch.eye(d, dtype=torch.float64), a64, alpha, "identity")
+    (y64 * seed).sum().backward()
+    hg = h.float().to(dev).requires_grad_(True)
+    ag = a.float().to(dev).requires_grad_(True)
+    s1, s2 = hg @ ag[0, :d], hg @ ag[0, d:]
+    y = ops.gat_aggregate(hg, s1, s2, A, alpha)
+    (y * seed.float().to(dev)).sum().backward()
+    assert relerr(y, y64.detach()) < REL
+    assert relerr(hg.grad, h64.grad) < REL
+    assert relerr(ag.grad, a64.grad) < REL
+    # edge scale: compare with a dense torch evaluation on the GPU in fp64
+    nnz = A.csr.nnz
+    m = (torch.rand(nnz, generator=gen) > 0.3).float().to(dev) / 0.7
+    crow = A.csr.rowptr.long()
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), crow[1:] - crow[:-1])
+    cols = A.csr.col.long()
+    hd = h.to(dev).requires_grad_(True)
+    t = (hd @ a.to(dev)[0, :d])[rows] + (hd @ a.to(dev)[0, d:])[cols]
+    w = torch.exp(-F.leaky_relu(t, alpha))
+    W = torch.zeros(n, dtype=torch.float64, device=dev).index_add(0, rows, w)
+    yd = torch.zeros(n, d, dtype=torch.float64, device=dev).index_add(0, rows, (w * m.double())[:, None] * hd[cols])
+    yd = yd / W[:, None]
+    (yd * seed.to(dev)).sum().backward()
+    hg2 = h.float().to(dev).requires_grad_(True)
+    y2 = ops.gat_aggregate(hg2, hg2 @ ag.detach()[0, :d], hg2 @ ag.detach()[0, d:], A, alpha, edge_scale=m)
+    (y2 * seed.float().to(dev)).sum().backward()
+    assert relerr(y2, yd.detach()) < REL
+    assert relerr(hg2.grad, hd.grad) < REL
+
+
+def test_gat_encoder_trains(dev):
+    """model2encoder['GAT'] (4 heads x 75) wired as in models/encoders.py:69-86 runs fwd/bwd and matches the oracle."""
+    from types import SimpleNamespace
+    from gnn_mtl_b200 import synth
+    from gnn_mtl_b200.adjacency import DeviceAdjacency
+    from gnn_mtl_b200.models.encoders import model2encoder
+    from oracle import ea_oracle as orc
+    n = 900
+    heads, tails = synth.make_powerlaw_graph(n, 8, seed=8)
+    chain = np.arange(n - 1)
+    heads, tails = np.concatenate([heads, chain]), np.concatenate([tails, chain + 1])
+    adj = DeviceAdjacency.from_heads_tails(n, torch.from_numpy(heads).to(dev), torch.from_numpy(tails).to(dev)).to_torch_coo()
+    args = SimpleNamespace(num_layers=3, dim=300, feat_dim=300, act="relu", n_heads=4, alpha=0.2, dropout=0.0,
+                           bias=1, cuda=0, device=dev, task="ea")
+    torch.manual_seed(0)
+    enc = model2encoder["GAT"](args).to(dev)
+    x = (torch.randn(n, 300) * 0.3).to(dev).requires_grad_(True)
+    y = enc.encode(x, adj)
+    assert y.shape == (n, 300)
+    y.square().sum().backward()
+    adj_cpu = orc.adjacency_torch_coo(n, heads, tails)
+    xc = x.detach().cpu().double().requires_grad_(True)
+    hcur = xc
+    for layer in enc.layers:
+        hs = [(att.W.detach().cpu().double(), att.a.detach().cpu().double()) for att in layer.attentions]
+        hcur = orc.gat_multihead(hcur, adj_cpu, hs, 0.2, "relu", True)
+    hcur.square().sum().backward()
+    assert relerr(y, hcur.detach()) < REL
+    assert relerr(x.grad, xc.grad) < 5e-4

@@ -129,3 +129,28 @@ def test_gromov_wasserstein_projection(golden_dir):
     T, gw = orc.gw_iterative(C1, C2, mu, nu, 0.02, 6)
     np.testing.assert_allclose(T.numpy(), g["T"], rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(float(gw), float(g["gw"]), rtol=1e-10)
+
+
+def test_gat_layer_forward_backward(golden_dir):
+    """oracle.gat_layer / gat_multihead reproduce layers/att_layers.py outputs and gradients."""
+    g = _load(golden_dir, "gat.npz")
+    adj = _adj(g)
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    W = torch.from_numpy(g["s_W"]).requires_grad_(True)
+    a = torch.from_numpy(g["s_a"]).requires_grad_(True)
+    y = orc.gat_layer(x, adj, W, a, 0.2, "elu")
+    (y * torch.from_numpy(g["s_seed"])).sum().backward()
+    np.testing.assert_allclose(y.detach().numpy(), g["s_y"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(x.grad.numpy(), g["s_dx"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(W.grad.numpy(), g["s_dW"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(a.grad.numpy(), g["s_da"], rtol=1e-4, atol=1e-5)
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    heads = [(torch.from_numpy(g["m_W%d" % i]).requires_grad_(True), torch.from_numpy(g["m_a%d" % i]).requires_grad_(True))
+             for i in range(4)]
+    y = orc.gat_multihead(x, adj, heads, 0.2, "relu", concat=True)
+    (y * torch.from_numpy(g["m_seed"])).sum().backward()
+    np.testing.assert_allclose(y.detach().numpy(), g["m_y"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(x.grad.numpy(), g["m_dx"], rtol=1e-4, atol=1e-5)
+    for i, (Wh, ah) in enumerate(heads):
+        np.testing.assert_allclose(Wh.grad.numpy(), g["m_dW%d" % i], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(ah.grad.numpy(), g["m_da%d" % i], rtol=1e-4, atol=1e-5)
