@@ -59,8 +59,10 @@ SIGNATURES = {
                                     _i64, _vp]),
     "eg_margin_loss_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp]),
     "eg_margin_loss_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),
-    "eg_gat_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
-    "eg_gat_bwd_edges": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eg_gat_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp,
+                           _i32, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "eg_gat_bwd_edges": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "eg_permute_edges": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 

@@ -402,7 +402,9 @@ class _GatAggregate(torch.autograd.Function):
         wsum = torch.empty(c.n_rows, dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):
             check(lib.eg_gat_fwd(ptr(c.rowptr), ptr(c.col), c.n_rows, ptr(h), h.shape[1], ptr(s1), ptr(s2),
-                                 float(alpha), ptr(edge_scale), ptr(y), ptr(wsum), stream()), "eg_gat_fwd")
+                                 float(alpha), ptr(edge_scale), ptr(y), ptr(wsum), c.threshold, ptr(c.seg_row),
+                                 ptr(c.seg_begin), ptr(c.seg_end), c.n_seg, ptr(c.long_rows), ptr(c.long_first),
+                                 c.n_long, ptr(c.scratch(h.shape[1] + 1)), stream()), "eg_gat_fwd")
         ctx.save_for_backward(h, s1, s2, y, wsum)
         ctx.adjacency, ctx.alpha, ctx.edge_scale = adjacency, float(alpha), edge_scale
         return y
@@ -421,7 +423,8 @@ class _GatAggregate(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.eg_gat_bwd_edges(ptr(c.rowptr), ptr(c.col), c.n_rows, c.n_cols, ptr(h), h.shape[1], ptr(s1),
                                        ptr(s2), ctx.alpha, ptr(ctx.edge_scale), ptr(y), ptr(wsum), ptr(dy),
-                                       ptr(p_edge), ptr(ds1), ptr(ds2), stream()), "eg_gat_bwd_edges")
+                                       ptr(p_edge), ptr(ds1), ptr(ds2), c.threshold, ptr(c.seg_row),
+                                       ptr(c.seg_begin), ptr(c.seg_end), c.n_seg, stream()), "eg_gat_bwd_edges")
             check(lib.eg_permute_edges(ptr(p_edge), ptr(ct.perm), c.nnz, ptr(p_t), stream()), "eg_permute_edges")
             dh = torch.empty_like(h)
             scratch = ct.scratch(h.shape[1])

@@ -225,11 +225,17 @@ int eg_margin_loss_bwd(const float* out, int64_t n, int d, const int64_t* left, 
  * CSR(A^T) whose values are p_edge permuted with eg_permute_edges(p_edge, perm_t).  d <= 512. */
 int eg_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n_rows, const float* h, int d,
                const float* s1, const float* s2, float alpha, const float* edge_scale,
-               float* out, float* wsum, eg_stream_t stream);
+               float* out, float* wsum,
+               /* hub-row segmentation, same meaning as eg_spmm's; seg_scratch holds n_seg * (d + 1) floats */
+               int long_row_threshold, const int32_t* seg_row, const int32_t* seg_begin,
+               const int32_t* seg_end, int64_t n_seg, const int32_t* long_rows, const int32_t* long_first,
+               int64_t n_long, float* seg_scratch, eg_stream_t stream);
 int eg_gat_bwd_edges(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols,
                      const float* h, int d, const float* s1, const float* s2, float alpha,
                      const float* edge_scale, const float* y, const float* wsum, const float* dy,
-                     float* p_edge, float* ds1, float* ds2, eg_stream_t stream);
+                     float* p_edge, float* ds1, float* ds2,
+                     int long_row_threshold, const int32_t* seg_row, const int32_t* seg_begin,
+                     const int32_t* seg_end, int64_t n_seg, eg_stream_t stream);
 int eg_permute_edges(const float* src, const int32_t* perm, int64_t n, float* dst, eg_stream_t stream);
 
 #ifdef __cplusplus
