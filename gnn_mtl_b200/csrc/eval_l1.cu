@@ -11,6 +11,8 @@
 // (16 B per pair against 600 DADDs per pair at d=300, i.e. noise).
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eg {
@@ -19,16 +21,17 @@ constexpr int kTile = 64;     // 64 x 64 distances per CTA
 constexpr int kKC = 32;       // k-chunk staged in shared memory
 constexpr int kPad = 66;      // row stride (doubles) of the [k][i] tiles: 528 B keeps 16-B alignment
 
-__global__ void __launch_bounds__(256, 2)
-l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict__ R, int64_t nR, int d,
-               double* __restrict__ D, int64_t ldD) {
-  __shared__ __align__(16) double Ls[kKC][kPad];
-  __shared__ __align__(16) double Rs[kKC][kPad];
-  const int tx = threadIdx.x & 15;   // columns j0 + 2*tx + {0,1} and j0 + 32 + 2*tx + {0,1}: 16-byte lane stride -> conflict-free LDS.128
-  const int ty = threadIdx.x >> 4;   // row group:    i = i0 + 4*ty .. +3
-  const int64_t i0 = (int64_t)blockIdx.y * kTile;
-  const int64_t j0 = (int64_t)blockIdx.x * kTile;
-  double acc[4][4];
+// acc[a][b] = sum_k |L[i0 + 4*ty + a, k] - R[j0 + col(b), k]| for one 64 x 64 tile, k ascending (SciPy's order).
+// Thread layout: tx = tid & 15 owns columns j0 + 2*tx + {0,1} and j0 + 32 + 2*tx + {0,1} (16-byte lane stride ->
+// conflict-free LDS.128), ty = tid >> 4 owns rows i0 + 4*ty .. +3.  Ends with a __syncthreads().
+__device__ __forceinline__ int l1_col_of(int tx, int b) { return 32 * (b >> 1) + 2 * tx + (b & 1); }
+
+__device__ __forceinline__ void l1_tile_accumulate(const float* __restrict__ L, int64_t nL,
+                                                   const float* __restrict__ R, int64_t nR, int d, int64_t i0,
+                                                   int64_t j0, double (*Ls)[kPad], double (*Rs)[kPad],
+                                                   double (&acc)[4][4]) {
+  const int tx = threadIdx.x & 15;
+  const int ty = threadIdx.x >> 4;
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -73,6 +76,19 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256, 2)
+l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict__ R, int64_t nR, int d,
+               double* __restrict__ D, int64_t ldD) {
+  __shared__ __align__(16) double Ls[kKC][kPad];
+  __shared__ __align__(16) double Rs[kKC][kPad];
+  const int tx = threadIdx.x & 15;
+  const int ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * kTile;
+  const int64_t j0 = (int64_t)blockIdx.x * kTile;
+  double acc[4][4];
+  l1_tile_accumulate(L, nL, R, nR, d, i0, j0, Ls, Rs, acc);
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     int64_t i = i0 + 4 * ty + a;
@@ -88,6 +104,75 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
         if (j + 1 < nR) dst[1] = acc[a][2 * h + 1];
       }
     }
+  }
+}
+
+// ---- streamed variants: the distance matrix is never stored ---------------------------------------
+// A CTA owns a 64-row strip and walks `tiles_per_cta` consecutive column tiles.
+
+// Rank counts of eg_rank_accumulate, taken straight from the accumulators.
+__global__ void __launch_bounds__(256, 2)
+l1_rank_fused_kernel(const float* __restrict__ L, int64_t nL, int64_t row0, const float* __restrict__ R, int64_t nR,
+                     int d, int tiles_per_cta, const double* __restrict__ diag, int32_t* __restrict__ rank_row,
+                     int32_t* __restrict__ rank_col) {
+  __shared__ __align__(16) double Ls[kKC][kPad];
+  __shared__ __align__(16) double Rs[kKC][kPad];
+  __shared__ int col_cnt_s[2][kTile];
+  const int tx = threadIdx.x & 15;
+  const int ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * kTile;
+  const int64_t n_col_tiles = (nR + kTile - 1) / kTile;
+  const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t_end = min(n_col_tiles, t_begin + tiles_per_cta);
+  double di[4];
+  int64_t gi[4];
+  int row_cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t i = i0 + 4 * ty + a;
+    gi[a] = row0 + i;                              // global row id == index of its true match
+    di[a] = (i < nL) ? diag[gi[a]] : 0.0;
+  }
+  if (threadIdx.x < 2 * kTile) (&col_cnt_s[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+  int buf = 0;
+  for (int64_t t = t_begin; t < t_end; ++t, buf ^= 1) {
+    const int64_t j0 = t * kTile;
+    double acc[4][4];
+    l1_tile_accumulate(L, nL, R, nR, d, i0, j0, Ls, Rs, acc);
+    int col_cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t j = j0 + l1_col_of(tx, b);
+      const bool col_ok = j < nR;
+      const double dj = col_ok ? __ldg(diag + j) : 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const bool ok = col_ok && (i0 + 4 * ty + a < nL);
+        const double v = acc[a][b];
+        row_cnt[a] += ok && ((v < di[a]) || (v == di[a] && j < gi[a]));
+        col_cnt[b] += ok && ((v < dj) || (v == dj && gi[a] < j));
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int c = col_cnt[b] + __shfl_xor_sync(0xffffffffu, col_cnt[b], 16);   // the warp's two row groups
+      if ((threadIdx.x & 16) == 0 && c) atomicAdd(&col_cnt_s[buf][l1_col_of(tx, b)], c);
+    }
+    __syncthreads();
+    if (threadIdx.x < kTile) {
+      const int c = col_cnt_s[buf][threadIdx.x];
+      if (c) { atomicAdd(&rank_col[j0 + threadIdx.x], c); col_cnt_s[buf][threadIdx.x] = 0; }
+    }
+    // no second barrier: the next tile adds into the other buffer, and l1_tile_accumulate's own barriers
+    // order this buffer's reset before its reuse two tiles later
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int c = row_cnt[a];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (tx == 0 && c && i0 + 4 * ty + a < nL) atomicAdd(&rank_row[gi[a]], c);
   }
 }
 
@@ -281,9 +366,270 @@ topk_rows_kernel(const double* __restrict__ D, int64_t ldD, int64_t n_cols, int 
   }
 }
 
+// ---- streamed per-row top-k ------------------------------------------------------------------------
+// A CTA keeps, for each of its 64 rows, the `want` smallest (key, index) pairs seen so far in shared memory
+// (unsorted, with the position of the current worst entry tracked).  After every tile each thread tests its 16
+// distances against its rows' worst entries; survivors (rare once the lists have warmed up: ~want*ln(n/want)
+// per row in total) go into a small per-row queue and are folded in by the row's quad of threads: replace the
+// worst entry, rescan for the new worst (4 lanes x want/4 entries + two shuffles).  The order is the total
+// order (value, index), so the result does not depend on arrival order and equals the stable argsort the
+// reference takes.  Lists are rank-sorted once at the end.
+constexpr int kRowQueue = 16;
+
+struct TopkSmem {
+  double (*Ls)[kPad];
+  double (*Rs)[kPad];
+  unsigned long long* list_key;   // [64][wp]
+  unsigned long long* q_key;      // [64][kRowQueue]
+  unsigned long long* worst_key;  // [64]
+  int* list_idx;                  // [64][wp]
+  int* q_idx;                     // [64][kRowQueue]
+  int* worst_idx;                 // [64]
+  int* worst_pos;                 // [64]
+  int* q_cnt;                     // [64]
+};
+
+__host__ __device__ inline size_t topk_smem_bytes(int wp) {
+  return 2 * sizeof(double) * kKC * kPad + (size_t)kTile * (wp + kRowQueue + 1) * 12 + (size_t)kTile * 8;
+}
+
+__device__ __forceinline__ TopkSmem carve_topk(unsigned char* base, int wp) {
+  TopkSmem m;
+  m.Ls = reinterpret_cast<double(*)[kPad]>(base);
+  m.Rs = reinterpret_cast<double(*)[kPad]>(base + sizeof(double) * kKC * kPad);
+  unsigned char* p = base + 2 * sizeof(double) * kKC * kPad;
+  m.list_key = reinterpret_cast<unsigned long long*>(p);  p += (size_t)kTile * wp * 8;
+  m.q_key = reinterpret_cast<unsigned long long*>(p);     p += (size_t)kTile * kRowQueue * 8;
+  m.worst_key = reinterpret_cast<unsigned long long*>(p); p += (size_t)kTile * 8;
+  m.list_idx = reinterpret_cast<int*>(p);                 p += (size_t)kTile * wp * 4;
+  m.q_idx = reinterpret_cast<int*>(p);                    p += (size_t)kTile * kRowQueue * 4;
+  m.worst_idx = reinterpret_cast<int*>(p);                p += (size_t)kTile * 4;
+  m.worst_pos = reinterpret_cast<int*>(p);                p += (size_t)kTile * 4;
+  m.q_cnt = reinterpret_cast<int*>(p);
+  return m;
+}
+
+__device__ __forceinline__ bool pair_less(unsigned long long ka, int ia, unsigned long long kb, int ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+__global__ void __launch_bounds__(256)
+l1_topk_stream_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict__ R, int64_t nR, int d,
+                      int tiles_per_cta, int want, int wp, unsigned long long* __restrict__ part_key,
+                      int* __restrict__ part_idx) {
+  extern __shared__ __align__(16) unsigned char topk_smem_raw[];
+  const TopkSmem m = carve_topk(topk_smem_raw, wp);
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;
+  const int ty = tid >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * kTile;
+  const int64_t n_col_tiles = (nR + kTile - 1) / kTile;
+  const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t_end = min(n_col_tiles, t_begin + tiles_per_cta);
+  for (int i = tid; i < kTile * wp; i += 256) { m.list_key[i] = ~0ull; m.list_idx[i] = 0x7fffffff; }
+  if (tid < kTile) {
+    m.worst_key[tid] = ~0ull; m.worst_idx[tid] = 0x7fffffff; m.worst_pos[tid] = 0; m.q_cnt[tid] = 0;
+  }
+  __syncthreads();
+  const int qrow = tid >> 2, qlane = tid & 3;          // drain: a quad of lanes per row
+  for (int64_t t = t_begin; t < t_end; ++t) {
+    const int64_t j0 = t * kTile;
+    double acc[4][4];
+    l1_tile_accumulate(L, nL, R, nR, d, i0, j0, m.Ls, m.Rs, acc);
+    // bit a*4+b set <=> acc[a][b] still beats the row's current worst entry
+    auto beats_worst = [&]() {
+      unsigned pending = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int row = 4 * ty + a;
+        if (i0 + row >= nL) continue;
+        const unsigned long long tk = m.worst_key[row];
+        const int ti = m.worst_idx[row];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int64_t j = j0 + l1_col_of(tx, b);
+          if (j < nR && pair_less(order_key(acc[a][b]), (int)j, tk, ti)) pending |= 1u << (a * 4 + b);
+        }
+      }
+      return pending;
+    };
+    unsigned pending = beats_worst();
+    while (__syncthreads_or(pending != 0)) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (pending & (1u << (a * 4 + b))) {
+            const int row = 4 * ty + a;
+            const int slot = atomicAdd(&m.q_cnt[row], 1);
+            if (slot < kRowQueue) {                    // queued: the drain below settles it for good
+              m.q_key[row * kRowQueue + slot] = order_key(acc[a][b]);
+              m.q_idx[row * kRowQueue + slot] = (int)(j0 + l1_col_of(tx, b));
+              pending &= ~(1u << (a * 4 + b));
+            }
+          }
+      __syncthreads();
+      {
+        const unsigned quad = 0xFu << (tid & 28);               // the four lanes of this row (tid & 31 & ~3)
+        const int n = min(m.q_cnt[qrow], kRowQueue);
+        unsigned long long* lk = m.list_key + qrow * wp;
+        int* li = m.list_idx + qrow * wp;
+        unsigned long long wk = m.worst_key[qrow];
+        int wi = m.worst_idx[qrow], wpos = m.worst_pos[qrow];
+        for (int e = 0; e < n; ++e) {
+          const unsigned long long key = m.q_key[qrow * kRowQueue + e];
+          const int idx = m.q_idx[qrow * kRowQueue + e];
+          if (!pair_less(key, idx, wk, wi)) continue;            // uniform across the quad
+          __syncwarp(quad);
+          if (qlane == 0) { lk[wpos] = key; li[wpos] = idx; }
+          __syncwarp(quad);
+          // new worst: maximum of the list under (key, idx, position)
+          unsigned long long bk = 0ull;
+          int bi = -1, bp = -1;
+          for (int p2 = qlane; p2 < want; p2 += 4) {
+            const unsigned long long k2 = lk[p2];
+            const int i2 = li[p2];
+            if (bp < 0 || pair_less(bk, bi, k2, i2) || (bk == k2 && bi == i2)) { bk = k2; bi = i2; bp = p2; }
+          }
+#pragma unroll
+          for (int o = 1; o < 4; o <<= 1) {
+            const unsigned long long ok2 = __shfl_xor_sync(quad, bk, o);
+            const int oi = __shfl_xor_sync(quad, bi, o);
+            const int op = __shfl_xor_sync(quad, bp, o);
+            const bool take = op >= 0 && (bp < 0 || pair_less(bk, bi, ok2, oi) || (bk == ok2 && bi == oi && op > bp));
+            if (take) { bk = ok2; bi = oi; bp = op; }
+          }
+          wk = bk; wi = bi; wpos = bp;
+        }
+        __syncwarp(quad);
+        if (qlane == 0) {
+          m.worst_key[qrow] = wk; m.worst_idx[qrow] = wi; m.worst_pos[qrow] = wpos; m.q_cnt[qrow] = 0;
+        }
+      }
+      __syncthreads();
+      if (pending) pending &= beats_worst();       // left out for lack of room: retry unless the bar has moved past them
+    }
+  }
+  __syncthreads();
+  // rank sort of each row's list by (key, idx, position) and write-out in order
+  for (int i = tid; i < kTile * want; i += 256) {
+    const int row = i / want, pos = i - row * want;
+    if (i0 + row >= nL) continue;
+    const unsigned long long* lk = m.list_key + row * wp;
+    const int* li = m.list_idx + row * wp;
+    const unsigned long long key = lk[pos];
+    const int idx = li[pos];
+    int rank = 0;
+    for (int p2 = 0; p2 < want; ++p2) {
+      const unsigned long long k2 = lk[p2];
+      const int i2 = li[p2];
+      rank += pair_less(k2, i2, key, idx) || (k2 == key && i2 == idx && p2 < pos);
+    }
+    const int64_t o = ((int64_t)blockIdx.x * nL + i0 + row) * want + rank;
+    part_key[o] = key;
+    part_idx[o] = idx;
+  }
+}
+
+// Merge the per-segment sorted lists of one row (thread = row) and emit entries [skip, skip + k).
+__global__ void topk_merge_kernel(const unsigned long long* __restrict__ part_key, const int* __restrict__ part_idx,
+                                  int64_t nL, int n_seg, int want, int skip, int k, int64_t n_cols,
+                                  int64_t* __restrict__ out_idx) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= nL) return;
+  int head[64];
+  for (int s = 0; s < n_seg; ++s) head[s] = 0;
+  const int avail = (int)min((int64_t)want, n_cols);
+  for (int pos = 0; pos < skip + k; ++pos) {
+    int64_t pick = -1;
+    if (pos < avail) {
+      int best = -1;
+      unsigned long long bk = ~0ull;
+      int bi = 0x7fffffff;
+      for (int s = 0; s < n_seg; ++s) {
+        if (head[s] >= want) continue;
+        const int64_t o = ((int64_t)s * nL + row) * want + head[s];
+        const unsigned long long key = part_key[o];
+        const int idx = part_idx[o];
+        if (idx != 0x7fffffff && (best < 0 || pair_less(key, idx, bk, bi))) { best = s; bk = key; bi = idx; }
+      }
+      if (best >= 0) { ++head[best]; pick = bi; }
+    }
+    if (pos >= skip) out_idx[row * k + (pos - skip)] = pick;
+  }
+}
+
+static int topk_segments(int64_t nL, int64_t nR, int* tiles_per_cta) {
+  const int64_t row_tiles = ceil_div(nL, kTile), col_tiles = ceil_div(nR, kTile);
+  int64_t n_seg = ceil_div((int64_t)(4 * 148), row_tiles);          // aim for >= 4 CTAs per SM in flight overall
+  n_seg = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_seg, col_tiles), 64));
+  const int64_t per = ceil_div(col_tiles, n_seg);
+  *tiles_per_cta = (int)per;
+  return (int)ceil_div(col_tiles, per);
+}
+
 }  // namespace eg
 
 extern "C" {
+
+int eg_l1_rank_fused(const float* L, int64_t nL, int64_t row0, const float* R, int64_t nR, int d,
+                     const double* diag, int32_t* rank_row, int32_t* rank_col, eg_stream_t stream_) {
+  using namespace eg;
+  if (nL < 0 || nR < 0 || row0 < 0 || d <= 0 || row0 + nL > nR) return EG_ERR_INVALID;
+  if (nL == 0 || nR == 0) return EG_OK;
+  if (!L || !R || !diag || !rank_row || !rank_col) return EG_ERR_INVALID;
+  const int64_t gy = ceil_div(nL, kTile), col_tiles = ceil_div(nR, kTile);
+  if (gy > 65535) return EG_ERR_UNSUPPORTED;
+  // column segments per strip: enough CTAs for ~8 per SM overall, at most one per column tile
+  int64_t n_seg = std::max<int64_t>(1, std::min<int64_t>(col_tiles, ceil_div((int64_t)(8 * 148), gy)));
+  const int per = (int)ceil_div(col_tiles, n_seg);
+  n_seg = ceil_div(col_tiles, (int64_t)per);
+  cudaStream_t s = as_stream(stream_);
+  EG_CUDA(cudaMemsetAsync(rank_row + row0, 0, sizeof(int32_t) * (size_t)nL, s));
+  dim3 grid((unsigned)n_seg, (unsigned)gy);
+  l1_rank_fused_kernel<<<grid, 256, 0, s>>>(L, nL, row0, R, nR, d, per, diag, rank_row, rank_col);
+  EG_LAUNCHED();
+  return EG_OK;
+}
+
+size_t eg_l1_topk_fused_workspace_bytes(int64_t nL, int64_t nR, int skip, int k) {
+  using namespace eg;
+  if (nL <= 0 || nR <= 0 || skip < 0 || k <= 0) return 0;
+  int per = 0;
+  const int n_seg = topk_segments(nL, nR, &per);
+  return align_up((size_t)n_seg * (size_t)nL * (size_t)(skip + k) * 8) +
+         align_up((size_t)n_seg * (size_t)nL * (size_t)(skip + k) * 4);
+}
+
+int eg_l1_topk_fused(const float* L, int64_t nL, const float* R, int64_t nR, int d, int skip, int k, void* ws,
+                     size_t ws_bytes, int64_t* out_idx, eg_stream_t stream_) {
+  using namespace eg;
+  if (nL < 0 || nR < 0 || d <= 0 || skip < 0 || k <= 0) return EG_ERR_INVALID;
+  const int want = skip + k;
+  if (want > 128 || nR >= (1ll << 31)) return EG_ERR_UNSUPPORTED;
+  if (nL == 0) return EG_OK;
+  if (!L || !R || !out_idx || !ws) return EG_ERR_INVALID;
+  if (ws_bytes < eg_l1_topk_fused_workspace_bytes(nL, nR, skip, k)) return EG_ERR_WORKSPACE;
+  const int64_t gy = ceil_div(nL, kTile);
+  if (gy > 65535) return EG_ERR_UNSUPPORTED;
+  int per = 0;
+  const int n_seg = topk_segments(nL, nR, &per);
+  unsigned long long* part_key = reinterpret_cast<unsigned long long*>(ws);
+  int* part_idx = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) +
+                                         align_up((size_t)n_seg * (size_t)nL * (size_t)want * 8));
+  const int wp = want | 1;                                   // odd row stride: conflict-free list columns
+  const size_t smem = topk_smem_bytes(wp);
+  cudaStream_t s = as_stream(stream_);
+  EG_CUDA(cudaFuncSetAttribute(l1_topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)n_seg, (unsigned)gy);
+  l1_topk_stream_kernel<<<grid, 256, smem, s>>>(L, nL, R, nR, d, per, want, wp, part_key, part_idx);
+  EG_LAUNCHED();
+  topk_merge_kernel<<<(unsigned)ceil_div(nL, 128), 128, 0, s>>>(part_key, part_idx, nL, n_seg, want, skip, k, nR,
+                                                                out_idx);
+  EG_LAUNCHED();
+  return EG_OK;
+}
+
 
 int eg_l1_matrix(const float* L, int64_t nL, const float* R, int64_t nR, int d, double* D, int64_t ldD,
                  eg_stream_t stream_) {

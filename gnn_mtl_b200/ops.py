@@ -110,14 +110,33 @@ def topk_rows(D, skip, k):
     return out
 
 
-def l1_ranks(L, R, block_bytes=None):
+FUSED_ROW_CHUNK = 65535 * 64      # rows per streamed launch (grid.y limit x 64-row strips)
+
+
+def l1_rank_fused(L_block, row0, R, diag, rank_row, rank_col):
+    """Streamed rank counts for rows [row0, row0 + len(L_block)) of the L1 matrix against all of R: nothing of
+    size rows x cols is stored.  rank_row[row0:...] is overwritten, rank_col accumulated."""
+    _lib.require_cuda(L_block, R, diag, rank_row, rank_col)
+    L_block, R = _f32c(L_block), _f32c(R)
+    with torch.cuda.device(R.device):
+        for c0 in range(0, L_block.shape[0], FUSED_ROW_CHUNK):
+            blk = L_block[c0:c0 + FUSED_ROW_CHUNK]
+            check(lib.eg_l1_rank_fused(ptr(blk), blk.shape[0], row0 + c0, ptr(R), R.shape[0], R.shape[1], ptr(diag),
+                                       ptr(rank_row), ptr(rank_col), stream()), "eg_l1_rank_fused")
+
+
+def l1_ranks(L, R, block_bytes=None, streamed=True):
     """Ranks of the diagonal (true match) per row and per column of the fp64 L1
-    matrix between L and R (same length)."""
+    matrix between L and R (same length).  ``streamed=False`` takes the two-kernel route through a stored
+    distance block (kept for cross-checking; bit-identical)."""
     n = L.shape[0]
     dev = L.device
     diag = l1_paired(L, R)
     rank_row = torch.zeros(n, dtype=torch.int32, device=dev)
     rank_col = torch.zeros(n, dtype=torch.int32, device=dev)
+    if streamed:
+        l1_rank_fused(L, 0, R, diag, rank_row, rank_col)
+        return rank_row, rank_col
     rows = l1_block_rows(n, block_bytes)
     buf = torch.empty(min(rows, n), n, dtype=torch.float64, device=dev)
     for r0 in range(0, n, rows):
@@ -157,8 +176,35 @@ def l1_argmins(L, R, block_bytes=None):
     return row_min, row_arg, col_min, col_arg
 
 
-def l1_topk(L, R, skip, k, block_bytes=None):
+# The streamed kernel serves skip + k <= 128, but its per-row lists cost shared memory (one CTA per SM beyond ~48
+# entries); measured on B200 it wins for short lists (top-10 over 30,000 x 200,000: 301 vs 383 ms) and loses for the
+# reference's neg_num = 125 (424 vs 385 ms), so longer lists keep the stored-block radix select.
+TOPK_FUSED_MAX = 32
+
+
+def l1_topk_fused(L, R, skip, k):
+    """Streamed per-row top-k by (distance, index): entries [skip, skip + k) of every row's stable argsort
+    (skip + k <= 128)."""
+    _lib.require_cuda(L, R)
+    L, R = _f32c(L), _f32c(R)
     nL, nR = L.shape[0], R.shape[0]
+    out = torch.empty(nL, k, dtype=torch.int64, device=L.device)
+    with torch.cuda.device(L.device):
+        for c0 in range(0, nL, FUSED_ROW_CHUNK):
+            blk = L[c0:c0 + FUSED_ROW_CHUNK]
+            nb = int(lib.eg_l1_topk_fused_workspace_bytes(blk.shape[0], nR, skip, k))
+            ws = torch.empty(max(nb, 1), dtype=torch.uint8, device=L.device)
+            check(lib.eg_l1_topk_fused(ptr(blk), blk.shape[0], ptr(R), nR, L.shape[1], skip, k, ptr(ws), nb,
+                                       ptr(out[c0:c0 + FUSED_ROW_CHUNK]), stream()), "eg_l1_topk_fused")
+    return out
+
+
+def l1_topk(L, R, skip, k, block_bytes=None, streamed=True):
+    nL, nR = L.shape[0], R.shape[0]
+    if streamed is True and skip + k <= TOPK_FUSED_MAX and nL > 0 and nR > 0:
+        return l1_topk_fused(L, R, skip, k)
+    if streamed == "force" and nL > 0 and nR > 0:
+        return l1_topk_fused(L, R, skip, k)
     rows = l1_block_rows(nR, block_bytes)
     buf = torch.empty(min(rows, max(nL, 1)), nR, dtype=torch.float64, device=L.device)
     outs = []

@@ -163,13 +163,8 @@ def get_hits_sharded(vec, test_pair, top_k=(1, 10, 50, 100), group=None):
     diag = all_gather_rows(diag_loc, n, group)
     rank_row = torch.zeros(n, dtype=torch.int32, device=vec.device)
     rank_col = torch.zeros(n, dtype=torch.int32, device=vec.device)
-    rows = ops.l1_block_rows(n)
     if r1 > r0:
-        buf = torch.empty(min(rows, r1 - r0), n, dtype=torch.float64, device=vec.device)
-        for s0 in range(r0, r1, rows):
-            s1 = min(r1, s0 + rows)
-            D = ops.l1_matrix(L_loc[s0 - r0:s1 - r0], R, out=buf[:s1 - s0])
-            ops.rank_accumulate(D, s0, diag, rank_row, rank_col)
+        ops.l1_rank_fused(L_loc, r0, R, diag, rank_row, rank_col)     # streamed: no rows x n block is stored
     rank_row, rank_col = merge_rank_counts(rank_row[r0:r1], rank_col, n, group)
     return _hits_dict(rank_row, rank_col, top_k, n)
 

@@ -132,6 +132,17 @@ int eg_argmin_accumulate(const double* D, int64_t ldD, int64_t row0, int64_t n_r
 int eg_topk_rows(const double* D, int64_t ldD, int64_t n_rows, int64_t n_cols,
                  int skip, int k, int64_t* out_idx /* [n_rows, k] */, eg_stream_t stream);
 
+/* Streamed variants of the three calls above: the fp64 distance matrix is never stored (16 B per pair of
+ * HBM traffic avoided; what BASELINE config 5's 1M x 1M evaluation needs).  Bit-identical results.
+ * eg_l1_rank_fused == eg_l1_matrix(L, R) + eg_rank_accumulate(row0, ...): rank_row[row0 .. row0+nL) is
+ * overwritten, rank_col accumulated.
+ * eg_l1_topk_fused == eg_l1_matrix + eg_topk_rows for skip + k <= 128. */
+int eg_l1_rank_fused(const float* L, int64_t nL, int64_t row0, const float* R, int64_t nR, int d,
+                     const double* diag, int32_t* rank_row, int32_t* rank_col, eg_stream_t stream);
+size_t eg_l1_topk_fused_workspace_bytes(int64_t nL, int64_t nR, int skip, int k);
+int eg_l1_topk_fused(const float* L, int64_t nL, const float* R, int64_t nR, int d, int skip, int k,
+                     void* ws, size_t ws_bytes, int64_t* out_idx, eg_stream_t stream);
+
 /* ---- (b) Sinkhorn, log domain --------------------------------------------------
  * One half-sweep ("pass") on a MATERIALISED cost (utils/ot_loss.py:53-55 and
  * SinkhornOT/sinkhorn_loss.py:197-201 in log form):

@@ -227,8 +227,10 @@ def test_l1_matrix_bit_exact_and_ranks(dev):
     L[200:205] = L[300:305]
     sim = orc.l1_matrix(L, R)
     rr, cr = orc.diagonal_ranks(sim)
-    gr, gc = ops.l1_ranks(torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev), block_bytes=900 * 8 * 128)
-    assert np.array_equal(gr.cpu().numpy(), rr) and np.array_equal(gc.cpu().numpy(), cr)
+    for streamed in (True, False):
+        gr, gc = ops.l1_ranks(torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev), block_bytes=900 * 8 * 128,
+                              streamed=streamed)
+        assert np.array_equal(gr.cpu().numpy(), rr) and np.array_equal(gc.cpu().numpy(), cr), streamed
 
 
 def test_hits_topk_argmin_vs_oracle_medium(dev):
@@ -243,14 +245,49 @@ def test_hits_topk_argmin_vs_oracle_medium(dev):
     anchors = kg["train"][:64, 0]
     want = orc.nearest_negatives(anchors, vec, 125)
     out = vec.to(dev)
-    got = ops.l1_topk(out[torch.from_numpy(anchors).to(dev)], out, 1, 125).reshape(-1).cpu().numpy()
-    assert np.array_equal(got, want)
+    for streamed in ("force", False):
+        got = ops.l1_topk(out[torch.from_numpy(anchors).to(dev)], out, 1, 125, streamed=streamed)
+        assert np.array_equal(got.reshape(-1).cpu().numpy(), want), streamed
     Lx, Rx = kg["x"][:2100], kg["x"][kg["e1"]:kg["e1"] + 2300]
     M = orc.l1_matrix(Lx, Rx)
     rmin, rarg, cmin, carg = ops.l1_argmins(torch.from_numpy(Lx).to(dev), torch.from_numpy(Rx).to(dev),
                                             block_bytes=2300 * 8 * 500)
     assert np.array_equal(rarg.cpu().numpy(), M.argmin(1)) and np.array_equal(carg.cpu().numpy(), M.argmin(0))
     assert np.array_equal(rmin.cpu().numpy(), M.min(1)) and np.array_equal(cmin.cpu().numpy(), M.min(0))
+
+
+@pytest.mark.parametrize("nL,nR,d,skip,k", [(1, 1, 1, 0, 1), (70, 131, 300, 0, 10), (257, 64, 33, 1, 63),
+                                            (300, 5, 16, 0, 10), (1500, 2100, 40, 1, 125), (5000, 3000, 24, 0, 10),
+                                            (40000, 700, 8, 2, 3)])
+def test_streamed_topk_and_ranks_with_ties(nL, nR, d, skip, k, dev):
+    """The streamed kernels (distance matrix never stored) against NumPy's stable argsort of the oracle's fp64
+    matrix and against the stored-matrix kernels: heavy exact ties (duplicated rows, coarse-grid coordinates),
+    ragged tile edges, fewer columns than skip + k, one and many column segments."""
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import ops
+    rng = np.random.default_rng(nL * 7 + nR)
+    L = (rng.integers(-3, 4, (nL, d)) * 0.25).astype(np.float32)         # coarse grid -> many equal distances
+    R = (rng.integers(-3, 4, (nR, d)) * 0.25).astype(np.float32)
+    if nR > 20:
+        R[5:12] = R[13:20]                                                # exact duplicate columns
+    Lg, Rg = torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)
+    got = ops.l1_topk(Lg, Rg, skip, k, streamed="force").cpu().numpy()
+    ref = ops.l1_topk(Lg, Rg, skip, k, streamed=False).cpu().numpy()
+    assert np.array_equal(got, ref)
+    sub = slice(0, min(nL, 600))
+    order = np.argsort(orc.l1_matrix(L[sub], R), axis=1, kind="stable")
+    want = np.full((order.shape[0], k), -1, dtype=np.int64)
+    take = order[:, skip:skip + k]
+    want[:, :take.shape[1]] = take
+    assert np.array_equal(got[sub], want)
+    n = min(nL, nR)
+    if n > 1:
+        rs, cs = ops.l1_ranks(Lg[:n], Rg[:n], streamed=True)
+        rm, cm = ops.l1_ranks(Lg[:n], Rg[:n], streamed=False)
+        assert torch.equal(rs, rm) and torch.equal(cs, cm)
+        if n <= 3000:
+            rr, cr = orc.diagonal_ranks(orc.l1_matrix(L[:n], R[:n]))
+            assert np.array_equal(rs.cpu().numpy(), rr) and np.array_equal(cs.cpu().numpy(), cr)
 
 
 # ------------------------------------------------------------------- sinkhorn --
