@@ -316,6 +316,9 @@ struct PersistState {
   double err;                // last marginal error evaluated
   double err2[128];          // one accumulator per check (sweeps 0,10,...)
   unsigned long long t_phase[8];   // ns spent by CTA 0 in C, barrier, R, barrier, U (diagnostic)
+  int fallback;              // scaling-domain kernel: a sum left the fp32 range -> caller redoes the solve in the log domain
+  int absorb_req;            // scaling-domain kernel: sweep (+1) at which every CTA folds u, v into its kernel entries
+  int absorbs;               // how many times that happened (diagnostic)
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -874,6 +877,350 @@ sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld
   if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = final_buf; st->err = err; }
 }
 
+// ---- scaling-domain continuation of the on-chip solve ---------------------------------------------------
+// After a few log-domain sweeps (sinkhorn_onchip_kernel) the potentials are close enough that the classic
+// Sinkhorn-Knopp scaling form is safe in fp32 *relative to them*: with Kt_ij = exp2(LU_i + LV_j - M_ij/reg)
+// held on chip (<= a_i, rows sum to a_i at the hand-over) the sweep becomes two mat-vecs
+//     v_j = b_j / sum_i Kt_ij u_i,      u_i = a_i / sum_j Kt_ij v_j
+// with NO exponential: one FMA per entry per pass instead of FMA + MUFU.ex2, one float of partials per column
+// instead of a (max, sum) pair.  The accepted iterate is (LU + log2 u, LV + log2 v), identical in exact
+// arithmetic to the log-domain recursion, same stop rule.  Safety: if |log2 u| or |log2 v| drifts past 32 every
+// CTA folds u, v into Kt and the potentials (absorb_req); if a sum is 0 / inf / nan the kernel raises `fallback`
+// and the host redoes the solve with the log-domain kernel.  All reductions run in a fixed order
+// (deterministic).
+
+// 8 values per lane -> lane l ends with the warp-wide sum of value (l & 7): 7 + 2 shuffles instead of 8 x 5
+__device__ __forceinline__ float warp_transpose_sum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int w = 4; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = hi ? v[k + w] : v[k];
+      const float send = hi ? v[k] : v[k + w];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  float t = v[0];
+  t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t;
+}
+
+constexpr int kScSlots = 40;   // per-row slots: [0, 8) register rows (RR used), [8, 40) shared-memory rows
+
+template <int RR>   // rows kept in registers (the rest of the CTA's row block lives in shared memory)
+__global__ void __launch_bounds__(kOcThreads, 1)
+sinkhorn_onchip_scaling_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld, float inv_reg,
+                               const float* __restrict__ a, const float* __restrict__ b,
+                               const float* __restrict__ log_u_in, const float* __restrict__ log_v_in,
+                               int start_iter, int max_iter, double stop_thr, float* __restrict__ part,
+                               float* __restrict__ v_buf, float* __restrict__ log_u_out,
+                               float* __restrict__ log_v_out, PersistState* __restrict__ st, int S_max,
+                               float kAbsorbLog2) {
+  extern __shared__ __align__(16) unsigned char smem_raw_o[];
+  const int nb = gridDim.x, cta = blockIdx.x;
+  const int rows_per = (int)((I + nb - 1) / nb);
+  const int64_t row0 = min(I, (int64_t)cta * rows_per);
+  const int R = (int)(min(I, row0 + rows_per) - row0);
+  const int S = min(R, S_max);                              // rows [0,S) in smem (S <= 32), [S,R) in registers
+  const int cols_per = (J + nb - 1) / nb;                   // <= 32 (host checks)
+  const int col0 = min(J, cta * cols_per), col1 = min(J, col0 + cols_per);
+  const int ncols = col1 - col0;
+  const int ng = J / 4;
+  float* u_s = reinterpret_cast<float*>(smem_raw_o);        // [40] current scaling, by slot
+  float* LU_s = u_s + kScSlots;                             // [40] log2 potential already folded into Kt, by slot
+  float* a_s = LU_s + kScSlots;                             // [40] row marginals, by slot
+  float* red = a_s + kScSlots;                              // [kOcWarps][40]
+  int* flag_s = reinterpret_cast<int*>(red + kOcWarps * kScSlots);   // [4]
+  float4* kt = reinterpret_cast<float4*>(flag_s + 4);       // [S][ng]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned int target = 0;
+  const float inv2 = inv_reg * kLog2e;
+
+  int gq[kOcQ];
+  bool gok[kOcQ];
+#pragma unroll
+  for (int q = 0; q < kOcQ; ++q) { gq[q] = tid + kOcThreads * q; gok[q] = gq[q] < ng; }
+  // slot -> local row: slot < 8: register row S + slot (live iff slot < RR and S + slot < R); else smem row slot - 8
+  const int my_row = (tid < 8) ? S + tid : tid - 8;
+  const bool my_live = (tid < kScSlots) && ((tid < 8) ? (tid < RR && my_row < R) : (my_row < S));
+  if (tid < kScSlots) {
+    u_s[tid] = 1.0f;
+    LU_s[tid] = my_live ? log_u_in[row0 + my_row] * kLog2e : 0.f;
+    a_s[tid] = my_live ? a[row0 + my_row] : 0.f;
+  }
+  if (tid < 4) flag_s[tid] = 0;
+  __syncthreads();
+  {
+    float4 lvq[kOcQ];
+#pragma unroll
+    for (int q = 0; q < kOcQ; ++q) {
+      lvq[q] = gok[q] ? reinterpret_cast<const float4*>(log_v_in)[gq[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      lvq[q].x *= kLog2e; lvq[q].y *= kLog2e; lvq[q].z *= kLog2e; lvq[q].w *= kLog2e;
+    }
+    for (int r = 0; r < S; ++r) {
+      const float4* src = reinterpret_cast<const float4*>(M + (row0 + r) * ld);
+      const float lu = LU_s[8 + r];
+#pragma unroll
+      for (int q = 0; q < kOcQ; ++q)
+        if (gok[q]) {
+          const float4 m = src[gq[q]];
+          kt[r * ng + gq[q]] = make_float4(ex2f(fmaf(-m.x, inv2, lu + lvq[q].x)), ex2f(fmaf(-m.y, inv2, lu + lvq[q].y)),
+                                           ex2f(fmaf(-m.z, inv2, lu + lvq[q].z)), ex2f(fmaf(-m.w, inv2, lu + lvq[q].w)));
+        }
+    }
+  }
+  float4 kreg[RR][kOcQ];
+#pragma unroll
+  for (int rr = 0; rr < RR; ++rr)
+#pragma unroll
+    for (int q = 0; q < kOcQ; ++q) {
+      kreg[rr][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gok[q] && (S + rr < R)) {
+        const float4 m = reinterpret_cast<const float4*>(M + (row0 + S + rr) * ld)[gq[q]];
+        float4 lv = reinterpret_cast<const float4*>(log_v_in)[gq[q]];
+        const float lu = LU_s[rr];
+        kreg[rr][q] = make_float4(ex2f(fmaf(-m.x, inv2, lu + lv.x * kLog2e)), ex2f(fmaf(-m.y, inv2, lu + lv.y * kLog2e)),
+                                  ex2f(fmaf(-m.z, inv2, lu + lv.z * kLog2e)), ex2f(fmaf(-m.w, inv2, lu + lv.w * kLog2e)));
+      }
+    }
+  // owned columns: warp 0, lane l < ncols
+  float LV_own = 0.f, v_own = 1.0f, b_own = 0.f;
+  if (warp == 0 && lane < ncols) { LV_own = log_v_in[col0 + lane] * kLog2e; b_own = b[col0 + lane]; }
+  __syncthreads();
+
+  int cpt = start_iter, sweeps = start_iter;
+  double err = 1.0;
+  // raised in phase U, published in the next phase R (between the same two grid barriers as every other flag
+  // write, so that all CTAs read one value)
+  bool u_big = false, u_bad = false;
+  const bool timer = (cta == 0 && tid == 0);
+  const int gqs0 = gok[0] ? gq[0] : 0, gqs1 = gok[1] ? gq[1] : 0;
+  for (cpt = start_iter; cpt < max_iter; ++cpt) {
+    const int nxt = (cpt & 1) ^ 1;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    if (timer) t0 = gtime();
+    // ---- C: partial column sums over my rows ---------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < kOcQ; ++q) {
+      if (!gok[q]) continue;
+      const float4* sbase = kt + gq[q];
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+      int r = 0;
+      for (; r + 3 < S; r += 4) {
+        const float4 k0 = sbase[r * ng], k1 = sbase[(r + 1) * ng], k2 = sbase[(r + 2) * ng], k3 = sbase[(r + 3) * ng];
+        const float u0 = u_s[8 + r], u1 = u_s[9 + r], u2 = u_s[10 + r], u3 = u_s[11 + r];
+        acc0.x = fmaf(k0.x, u0, acc0.x); acc0.y = fmaf(k0.y, u0, acc0.y); acc0.z = fmaf(k0.z, u0, acc0.z); acc0.w = fmaf(k0.w, u0, acc0.w);
+        acc1.x = fmaf(k1.x, u1, acc1.x); acc1.y = fmaf(k1.y, u1, acc1.y); acc1.z = fmaf(k1.z, u1, acc1.z); acc1.w = fmaf(k1.w, u1, acc1.w);
+        acc0.x = fmaf(k2.x, u2, acc0.x); acc0.y = fmaf(k2.y, u2, acc0.y); acc0.z = fmaf(k2.z, u2, acc0.z); acc0.w = fmaf(k2.w, u2, acc0.w);
+        acc1.x = fmaf(k3.x, u3, acc1.x); acc1.y = fmaf(k3.y, u3, acc1.y); acc1.z = fmaf(k3.z, u3, acc1.z); acc1.w = fmaf(k3.w, u3, acc1.w);
+      }
+      for (; r < S; ++r) {
+        const float4 k0 = sbase[r * ng];
+        const float u0 = u_s[8 + r];
+        acc0.x = fmaf(k0.x, u0, acc0.x); acc0.y = fmaf(k0.y, u0, acc0.y); acc0.z = fmaf(k0.z, u0, acc0.z); acc0.w = fmaf(k0.w, u0, acc0.w);
+      }
+#pragma unroll
+      for (int rr = 0; rr < RR; ++rr) {
+        const float u0 = u_s[rr];
+        acc1.x = fmaf(kreg[rr][q].x, u0, acc1.x); acc1.y = fmaf(kreg[rr][q].y, u0, acc1.y);
+        acc1.z = fmaf(kreg[rr][q].z, u0, acc1.z); acc1.w = fmaf(kreg[rr][q].w, u0, acc1.w);
+      }
+      reinterpret_cast<float4*>(part + (int64_t)cta * J)[gq[q]] =
+          make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
+    }
+    if (timer) t1 = gtime();
+    grid_barrier(&st->barrier, target, nb);
+    if (timer) t2 = gtime();
+    // ---- R: total column sums for my slice of columns -> v ---------------------------------------------
+    const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
+    const int slot = check ? ((cpt - 1) / 10) & 127 : 0;
+    {
+      float sum = 0.f;
+      if (lane < ncols) {
+        float pv[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const int pidx = warp + kOcWarps * k;
+          pv[k] = (pidx < nb) ? __ldcg(part + (int64_t)pidx * J + col0 + lane) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sum += pv[k];
+      }
+      red[warp * kScSlots + lane] = sum;
+    }
+    __syncthreads();
+    float v_cand = 1.0f;
+    if (warp == 0) {
+      double d2 = 0.0;
+      bool bad = u_bad, big = u_big;
+      if (lane < ncols) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < kOcWarps; ++w2) tot += red[w2 * kScSlots + lane];
+        if (check) {
+          const double d = (double)(v_own * tot) - (double)b_own;
+          d2 = d * d;
+        }
+        v_cand = b_own / tot;
+        bad = bad || !(tot > 0.f) || !(v_cand < CUDART_INF_F) || !(v_cand > 0.f);
+        big = big || fabsf(lg2f(v_cand)) > kAbsorbLog2;
+        v_buf[(int64_t)nxt * J + col0 + lane] = v_cand;
+      }
+      if (check) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        if (lane == 0 && d2 != 0.0) atomicAdd(&st->err2[slot], d2);
+      }
+      if (__any_sync(0xffffffffu, bad) && lane == 0) st->fallback = 1;
+      if (__any_sync(0xffffffffu, big) && lane == 0) st->absorb_req = cpt + 1;
+    }
+    if (timer) t3 = gtime();
+    grid_barrier(&st->barrier, target, nb);
+    if (timer) t4 = gtime();
+    // the new v (written by its owners before the barrier) is requested first so that its L2 round trip overlaps
+    // the flag / error reads below
+    float4 vq[kOcQ];
+    {
+      const float4* src = reinterpret_cast<const float4*>(v_buf + (int64_t)nxt * J);
+#pragma unroll
+      for (int q = 0; q < kOcQ; ++q) {
+        vq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gok[q])
+          asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(vq[q].x), "=f"(vq[q].y), "=f"(vq[q].z), "=f"(vq[q].w) : "l"(src + gq[q]) : "memory");
+      }
+    }
+    int fb, areq;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(fb) : "l"(&st->fallback) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(areq) : "l"(&st->absorb_req) : "memory");
+    double e2 = 0.0;
+    if (check) asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(e2) : "l"(&st->err2[slot]) : "memory");
+    if (fb) break;
+    if (check) {
+      err = sqrt(e2);
+      if (!(err > stop_thr)) break;                    // keep (u, v_own): sweep cpt never happened
+    }
+    v_own = v_cand;
+    const bool absorb = (areq == cpt + 1);
+    if (timer) st->t_phase[5] += gtime() - t4;
+    // ---- U: row sums with the new v -> u -----------------------------------------------------------------
+    // register rows, then the shared-memory rows in batches of 8 (two blocks of 4 rows: 8 LDS.128 in flight,
+    // unconditional with a clamped row; dead column groups carry v = 0), each batch reduced across the warp
+    // with the 8-value transpose
+    {
+      // all dot products first (register rows + shared-memory rows 0..23, clamped / zero-selected, so the loads
+      // are unconditional and deep in flight), then the four 8-value transposes back to back so their shuffle
+      // latencies overlap; rows 24..31 (only when S > 24) go through a separate, uniform-branch batch
+      float pr[8], pb[3][8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pr[k] = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < RR; ++rr)
+#pragma unroll
+        for (int q = 0; q < kOcQ; ++q)
+          pr[rr] += (kreg[rr][q].x * vq[q].x + kreg[rr][q].y * vq[q].y) + (kreg[rr][q].z * vq[q].z + kreg[rr][q].w * vq[q].w);
+      if (timer) st->t_phase[6] += gtime() - t4;
+      const int last_row = max(S, 1) - 1;          // a CTA past the end of the matrix has S == 0: stay inside kt
+      auto rows4 = [&](int r0, float (&dst)[8], int off) {
+        float4 k0[4];
+        float dot[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k0[u] = kt[min(r0 + u, last_row) * ng + gqs0];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          dot[u] = (k0[u].x * vq[0].x + k0[u].y * vq[0].y) + (k0[u].z * vq[0].z + k0[u].w * vq[0].w);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k0[u] = kt[min(r0 + u, last_row) * ng + gqs1];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dot[u] += (k0[u].x * vq[1].x + k0[u].y * vq[1].y) + (k0[u].z * vq[1].z + k0[u].w * vq[1].w);
+          dst[off + u] = (r0 + u < S) ? dot[u] : 0.f;
+        }
+      };
+#pragma unroll
+      for (int batch = 0; batch < 3; ++batch) {
+        rows4(batch * 8, pb[batch], 0);
+        rows4(batch * 8 + 4, pb[batch], 4);
+      }
+      const float tr = warp_transpose_sum8(pr, lane);
+      const float t0 = warp_transpose_sum8(pb[0], lane);
+      const float t1 = warp_transpose_sum8(pb[1], lane);
+      const float t2 = warp_transpose_sum8(pb[2], lane);
+      if (lane < 8) {
+        red[warp * kScSlots + lane] = tr;
+        red[warp * kScSlots + 8 + lane] = t0;
+        red[warp * kScSlots + 16 + lane] = t1;
+        red[warp * kScSlots + 24 + lane] = t2;
+      }
+      if (S > 24) {
+        rows4(24, pr, 0);
+        rows4(28, pr, 4);
+        const float t3 = warp_transpose_sum8(pr, lane);
+        if (lane < 8) red[warp * kScSlots + 32 + lane] = t3;
+      } else if (lane < 8) {
+        red[warp * kScSlots + 32 + lane] = 0.f;
+      }
+    }
+    if (timer) st->t_phase[7] += gtime() - t4;
+    __syncthreads();
+    if (tid < kScSlots) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kOcWarps; ++w2) tot += red[w2 * kScSlots + tid];
+      if (my_live) {
+        const float u = a_s[tid] / tot;
+        if (!(tot > 0.f) || !(u < CUDART_INF_F) || !(u > 0.f)) atomicOr(&flag_s[0], 1);
+        if (fabsf(lg2f(u)) > kAbsorbLog2) atomicOr(&flag_s[1], 1);
+        u_s[tid] = u;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // only warp 0 (phase R, epilogue) consumes these
+      u_bad = u_bad || (flag_s[0] != 0);
+      u_big = (flag_s[1] != 0);
+      __syncwarp();
+      if (lane == 0) flag_s[1] = 0;                    // next writers are two grid barriers away
+    }
+    if (absorb) {
+      // fold u, v into the on-chip kernel entries and the potentials; scalings restart from 1
+#pragma unroll
+      for (int q = 0; q < kOcQ; ++q) {
+        if (!gok[q]) continue;
+#pragma unroll
+        for (int rr = 0; rr < RR; ++rr) {
+          const float u0 = u_s[rr];
+          kreg[rr][q].x *= u0 * vq[q].x; kreg[rr][q].y *= u0 * vq[q].y;
+          kreg[rr][q].z *= u0 * vq[q].z; kreg[rr][q].w *= u0 * vq[q].w;
+        }
+        for (int r = 0; r < S; ++r) {
+          const float u0 = u_s[8 + r];
+          float4 k4 = kt[r * ng + gq[q]];
+          k4.x *= u0 * vq[q].x; k4.y *= u0 * vq[q].y; k4.z *= u0 * vq[q].z; k4.w *= u0 * vq[q].w;
+          kt[r * ng + gq[q]] = k4;
+        }
+      }
+      __syncthreads();
+      if (my_live) { LU_s[tid] += log2f(u_s[tid]); u_s[tid] = 1.0f; }
+      if (warp == 0 && lane < ncols) { LV_own += log2f(v_own); v_own = 1.0f; }
+      u_big = false;
+      if (cta == 0 && tid == 0) st->absorbs += 1;
+      __syncthreads();
+    }
+    sweeps = cpt + 1;
+    if (timer) {
+      st->t_phase[0] += t1 - t0; st->t_phase[1] += t2 - t1; st->t_phase[2] += t3 - t2;
+      st->t_phase[3] += t4 - t3; st->t_phase[4] += gtime() - t4;
+    }
+  }
+  __syncthreads();
+  if (u_bad && tid == 0) st->fallback = 1;             // last sweep's row sums: no later phase R to publish it
+  if (my_live) log_u_out[row0 + my_row] = (LU_s[tid] + log2f(u_s[tid])) * kLn2;
+  if (warp == 0 && lane < ncols) log_v_out[col0 + lane] = (LV_own + log2f(v_own)) * kLn2;
+  if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = 0; st->err = err; }
+}
+
 template <typename T>
 struct SolveWs {
   T *log_a, *log_b, *lv_alt, *col_lse;
@@ -904,6 +1251,12 @@ static SolveWs<T> carve_solve(void* ws, int64_t I, int64_t J) {
 int g_tune_persistent = 1;   // eg_debug_set(3, 0) forces the streaming path
 int g_tune_resident = 1;     // eg_debug_set(4, 0) keeps no rows of M in shared memory
 int g_tune_onchip = 1;       // eg_debug_set(5, 0) disables the fully on-chip fp32 kernel
+int g_tune_scaling = 1;      // eg_debug_set(7, 0) keeps the whole on-chip solve in the log domain
+int g_tune_absorb_milli = 32000;   // eg_debug_set(10, x): fold u, v into the kernel once |log2| exceeds x / 1000
+int g_tune_force_fallback = 0;     // eg_debug_set(11, 1): treat every scaling-domain solve as failed (tests the redo path)
+int g_sinkhorn_fallbacks = 0;
+int g_sinkhorn_absorbs = 0;
+constexpr int kWarmSweeps = 4;   // log-domain sweeps before the scaling-domain kernel takes over
 
 // One cooperative launch for the whole solve when the shape allows it.
 template <typename T>
@@ -938,31 +1291,84 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
         const int TB = 256;
         log_kernel<T><<<(unsigned)ceil_div(I, TB), TB, 0, s>>>(a, I, w.log_a); EG_LAUNCHED();
         log_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(b, J, w.log_b); EG_LAUNCHED();
-        fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log2((double)J))); EG_LAUNCHED();
-        EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
         float inv_reg = (float)(1.0 / reg);
         int64_t ld = J;
         int Ji = (int)J;
-        void* args[] = {(void*)&M, (void*)&I, (void*)&Ji, (void*)&ld, (void*)&inv_reg, (void*)&w.log_a,
-                        (void*)&w.log_b, (void*)&b, (void*)&max_iter, (void*)&stop_thr, (void*)&w.part_m,
-                        (void*)&w.part_s, (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&w.state,
-                        (void*)&S_max};
-        EG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)sms), dim3(kOcThreads), args, smem, s));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
         PersistState host_state;
-        EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(int) * 3 + sizeof(double) + 4, cudaMemcpyDeviceToHost, s));
-        EG_CUDA(cudaStreamSynchronize(s));
+        auto run_log = [&](int iters) -> int {
+          fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log2((double)J))); EG_LAUNCHED();
+          EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
+          void* args[] = {(void*)&M, (void*)&I, (void*)&Ji, (void*)&ld, (void*)&inv_reg, (void*)&w.log_a,
+                          (void*)&w.log_b, (void*)&b, (void*)&iters, (void*)&stop_thr, (void*)&w.part_m,
+                          (void*)&w.part_s, (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&w.state,
+                          (void*)&S_max};
+          EG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)sms), dim3(kOcThreads), args, smem, s));
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+          EG_CUDA(cudaStreamSynchronize(s));
+          return EG_OK;
+        };
+        auto report = [&](const char* what) {
+          if (!getenv("EG_PERSIST_TIMING") || host_state.sweeps <= 0) return;
+          const PersistState& full = host_state;
+          fprintf(stderr, "[eagraft] on-chip sinkhorn %s (S=%d): %d sweeps, %d absorptions, fallback %d; CTA0 us/sweep: C %.2f | bar %.2f | R %.2f | bar %.2f | U %.2f (U marks: %.2f, %.2f, %.2f)\n",
+                  what, S_max, full.sweeps, full.absorbs, full.fallback, full.t_phase[0] / 1e3 / full.sweeps,
+                  full.t_phase[1] / 1e3 / full.sweeps, full.t_phase[2] / 1e3 / full.sweeps,
+                  full.t_phase[3] / 1e3 / full.sweeps, full.t_phase[4] / 1e3 / full.sweeps,
+                  full.t_phase[5] / 1e3 / full.sweeps, full.t_phase[6] / 1e3 / full.sweeps,
+                  full.t_phase[7] / 1e3 / full.sweeps);
+        };
+        bool done = false;
+        if (g_tune_scaling && max_iter >= kWarmSweeps + 8 && ceil_div(J, (int64_t)sms) <= 32) {
+          int rc = run_log(kWarmSweeps);
+          if (rc) return rc;
+          report("log-domain warm-up");
+          if (host_state.sweeps < kWarmSweeps) {
+            done = true;                                  // the stop rule fired inside the warm-up
+          } else {
+            // hand-over copies: the scaling kernel reads every CTA's potentials while others may already write theirs
+            EG_CUDA(cudaMemcpyAsync(w.log_a, log_u, sizeof(T) * (size_t)I, cudaMemcpyDeviceToDevice, s));
+            EG_CUDA(cudaMemcpyAsync(w.lv_alt, log_v, sizeof(T) * (size_t)J, cudaMemcpyDeviceToDevice, s));
+            EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
+            // this kernel's fixed shared memory is smaller than the log-domain one's, so more rows fit and fewer
+            // have to live in registers
+            const size_t fixed2 = sizeof(float) * (size_t)(3 * kScSlots + kScSlots * kOcWarps + 4);
+            const int64_t fit2 = std::min<int64_t>(32, ((int64_t)max_smem - 1024 - (int64_t)fixed2) /
+                                                           (int64_t)(sizeof(float) * (size_t)J));
+            int S2 = (int)std::min<int64_t>(rows_per, fit2);
+            const bool rr2 = rows_per - S2 <= 2;
+            if (!rr2) S2 = S_max;                       // fall back to the 5-register-row split
+            auto kern2 = rr2 ? sinkhorn_onchip_scaling_kernel<2> : sinkhorn_onchip_scaling_kernel<kOcRR>;
+            const size_t smem2 = fixed2 + sizeof(float) * (size_t)J * (size_t)S2;
+            EG_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            int start = kWarmSweeps;
+            float absorb_log2 = (float)g_tune_absorb_milli / 1000.0f;
+            void* args2[] = {(void*)&M, (void*)&I, (void*)&Ji, (void*)&ld, (void*)&inv_reg, (void*)&a, (void*)&b,
+                             (void*)&w.log_a, (void*)&w.lv_alt, (void*)&start, (void*)&max_iter, (void*)&stop_thr,
+                             (void*)&w.part_m, (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&w.state,
+                             (void*)&S2, (void*)&absorb_log2};
+            EG_CUDA(cudaLaunchCooperativeKernel((void*)kern2, dim3((unsigned)sms), dim3(kOcThreads), args2, smem2, s));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+            EG_CUDA(cudaStreamSynchronize(s));
+            report("scaling-domain");
+            g_sinkhorn_absorbs = host_state.absorbs;
+            if (host_state.fallback || g_tune_force_fallback) {
+              ++g_sinkhorn_fallbacks;
+              // w.log_a was used as a hand-over buffer: restore log a for the log-domain kernel
+              log_kernel<T><<<(unsigned)ceil_div(I, TB), TB, 0, s>>>(a, I, w.log_a); EG_LAUNCHED();
+            } else {
+              done = true;
+            }
+          }
+        }
+        if (!done) {
+          int rc = run_log(max_iter);
+          if (rc) return rc;
+          report("log-domain");
+        }
         if (h_sweeps) *h_sweeps = host_state.sweeps;
         if (h_err) *h_err = host_state.err;
-        if (getenv("EG_PERSIST_TIMING")) {
-          PersistState full;
-          cudaMemcpy(&full, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost);
-          fprintf(stderr, "[eagraft] on-chip sinkhorn (S=%d): %d sweeps; CTA0 us/sweep: C %.2f | bar %.2f | R %.2f | bar %.2f | U %.2f (lv loaded %.2f, reg rows %.2f, smem row %.2f)\n",
-                  S_max, full.sweeps, full.t_phase[0] / 1e3 / full.sweeps, full.t_phase[1] / 1e3 / full.sweeps,
-                  full.t_phase[2] / 1e3 / full.sweeps, full.t_phase[3] / 1e3 / full.sweeps,
-                  full.t_phase[4] / 1e3 / full.sweeps, full.t_phase[5] / 1e3 / full.sweeps,
-                  full.t_phase[6] / 1e3 / full.sweeps, full.t_phase[7] / 1e3 / full.sweeps);
-        }
         *used = true;
         return EG_OK;
       }

@@ -24,6 +24,11 @@ int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelin
 extern int g_tune_persistent;
 extern int g_tune_resident;
 extern int g_tune_onchip;
+extern int g_tune_scaling;
+extern int g_sinkhorn_fallbacks;
+extern int g_sinkhorn_absorbs;
+extern int g_tune_absorb_milli;
+extern int g_tune_force_fallback;
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
 
 struct Epilogue {
@@ -428,6 +433,11 @@ int eg_debug_set(int key, int value) {
   else if (key == 4) eg::g_tune_resident = value;
   else if (key == 5) eg::g_tune_onchip = value;
   else if (key == 6) eg::g_tune_spmm_persist = value;
+  else if (key == 7) eg::g_tune_scaling = value;                  // 0: log-domain on-chip Sinkhorn only
+  else if (key == 8) return eg::g_sinkhorn_fallbacks;             // query: scaling-domain solves redone in the log domain
+  else if (key == 9) return eg::g_sinkhorn_absorbs;               // query: absorptions in the last scaling-domain solve
+  else if (key == 10) eg::g_tune_absorb_milli = value;
+  else if (key == 11) eg::g_tune_force_fallback = value;
   else return EG_ERR_INVALID;
   return EG_OK;
 }

@@ -51,6 +51,48 @@ def test_sinkhorn_dispatch_branches_agree_with_oracle(I, J, dev):
         assert relerr(r, results[0]) < 1e-5
 
 
+@pytest.mark.parametrize("I,J,reg,iters", [(3000, 3000, 0.01, 120), (2500, 3000, 0.02, 64), (1200, 1600, 0.05, 40)])
+def test_sinkhorn_scaling_domain_continuation(I, J, reg, iters, dev):
+    """The scaling-domain on-chip kernel (default for the reference's 3000 x 3000 batch) against the fp64 oracle
+    and against the all-log-domain kernel; with the fold-into-kernel step forced to fire (tiny threshold) and
+    with the redo-in-log-domain path forced."""
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import _lib
+    from gnn_mtl_b200.utils.ot_loss import sinkhorn
+    M, a, b = _problem(I, J, seed=J + iters)
+    M = M * 1.5
+    _, loss_ref, ref = orc.sinkhorn_scaling(a, b, M, reg, numItermax=iters, stopThr=-1.0, return_info=True)
+    dbg = _lib.lib.eg_debug_set
+    out = {}
+    try:
+        for name, knobs in (("scaling", {}), ("log", {7: 0}), ("absorb_often", {10: 10}), ("forced_redo", {11: 1})):
+            for key, val in knobs.items():
+                dbg(key, val)
+            fallbacks0 = dbg(8, 0)
+            info = {}
+            _, loss = sinkhorn(a.to(dev), b.to(dev), M.to(dev), reg, numItermax=iters, stopThr=-1.0, return_plan=False,
+                               info=info)
+            assert info["sweeps"] == iters, name
+            # potentials are fixed up to the (c, -c) shift the iteration itself leaves free: compare u_i + v_j
+            got = info["log_u"].double().cpu()[:, None] + info["log_v"].double().cpu()[None, :64]
+            want = ref["log_u"].double()[:, None] + ref["log_v"].double()[None, :64]
+            assert float((got - want).abs().max()) < 2e-4 * max(1.0, float(want.abs().max())), name
+            assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < 1e-4, name
+            if name == "absorb_often":
+                assert dbg(9, 0) > 0                      # the fold step really ran
+            if name == "forced_redo":
+                assert dbg(8, 0) == fallbacks0 + 1
+            if name == "scaling":
+                assert dbg(8, 0) == fallbacks0           # and did not need the redo
+            out[name] = info["log_u"].double().cpu()
+            for key in knobs:
+                dbg(key, {7: 1, 10: 32000, 11: 0}[key])
+    finally:
+        dbg(7, 1); dbg(10, 32000); dbg(11, 0)
+    assert float((out["forced_redo"] - out["log"]).abs().max()) == 0.0     # the redo IS the log-domain kernel
+    assert relerr(out["scaling"], out["log"]) < 1e-4 and relerr(out["absorb_often"], out["log"]) < 1e-4
+
+
 def test_sinkhorn_fp64_persistent_vs_streaming(dev):
     from oracle import ea_oracle as orc
     from gnn_mtl_b200 import _lib
