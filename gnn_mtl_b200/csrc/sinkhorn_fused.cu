@@ -241,6 +241,29 @@ __global__ void split_tf32_kernel(const float* __restrict__ X, int64_t n, int d,
   lo[idx] = __uint_as_float(lb);
 }
 
+// Vector path (d % 4 == 0, 16-byte aligned rows): one float4 of the padded row per thread, streaming loads/stores.
+__global__ void split_tf32_vec4_kernel(const float4* __restrict__ X, int64_t n, int d4, int dp4, float4* __restrict__ hi,
+                                       float4* __restrict__ lo) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * dp4) return;
+  const int64_t r = idx / dp4;
+  const int k = (int)(idx - r * dp4);
+  const float4 x = (k < d4) ? ld_stream_f4(X + r * d4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  float h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xs[e]));
+    h[e] = __uint_as_float(hb);
+    const float rem = xs[e] - h[e];   // exact in fp32
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+    l[e] = __uint_as_float(lb);
+  }
+  __stcs(hi + idx, make_float4(h[0], h[1], h[2], h[3]));
+  __stcs(lo + idx, make_float4(l[0], l[1], l[2], l[3]));
+}
+
 static int pick_splits(int64_t nA, int64_t nB) {
   int64_t row_blocks = ceil_div(nA, kFT);
   int64_t want = ceil_div((int64_t)kNumSMs * 2, row_blocks);   // >= 2 CTAs per SM overall
@@ -270,7 +293,13 @@ int eg_split_tf32(const float* X, int64_t n, int d, int d_pad, float* hi, float*
   if (n < 0 || d <= 0 || d_pad < d || d_pad % 8 != 0) return EG_ERR_INVALID;
   if (n == 0) return EG_OK;
   if (!X || !hi || !lo) return EG_ERR_INVALID;
-  split_tf32_kernel<<<(unsigned)ceil_div(n * d_pad, 256), 256, 0, as_stream(stream_)>>>(X, n, d, d_pad, hi, lo);
+  if (d % 4 == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
+    split_tf32_vec4_kernel<<<(unsigned)ceil_div(n * (d_pad / 4), 256), 256, 0, as_stream(stream_)>>>(
+        reinterpret_cast<const float4*>(X), n, d / 4, d_pad / 4, reinterpret_cast<float4*>(hi),
+        reinterpret_cast<float4*>(lo));
+  } else {
+    split_tf32_kernel<<<(unsigned)ceil_div(n * d_pad, 256), 256, 0, as_stream(stream_)>>>(X, n, d, d_pad, hi, lo);
+  }
   EG_LAUNCHED();
   return EG_OK;
 }

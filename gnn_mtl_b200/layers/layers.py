@@ -87,6 +87,7 @@ class _Aggregate(torch.autograd.Function):
 
 
 USE_TCGEN05_GEMM = True   # dense layer products on the 3xTF32 tcgen05 tiles; False -> everything on cuBLAS fp32
+USE_TCGEN05_DW = True     # dW = dHᵀ·x on the MN-major split-K tcgen05 kernel; False -> cuBLAS fp32 batched split-K
 
 
 def _weight_grad(d_hidden, x):
@@ -109,39 +110,58 @@ class _DenseProducts(torch.autograd.Function):
     pre-activations out of ~10^7, and each flip moves gradient entries by ~1e-3 relative — outside
     the 1e-4 parity bar.  So `hidden` stays on cuBLAS fp32 when the layer's activation is ReLU
     (`exact_hidden`), and goes through the tensor-core kernel otherwise; `gate_pre` and
-    dx = [dH | d_gate]·[Wᵀ | G]ᵀ always do.  dW = dHᵀ·x and db stay on cuBLAS / a reduction."""
+    dx = [dH | d_gate]·[Wᵀ | G]ᵀ always do.  dW = dHᵀ·x runs on the MN-major split-K tensor-core kernel from the
+    same hi/lo splits (x's is kept from the forward pass, dH's is shared with dx); db is a reduction."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, gate_w, gate_b, exact_hidden):
         n_out = weight.shape[0]
         gate_pre = None
+        x_split = None                      # hi/lo split of x: made once, reused by dW = dHᵀ·x in backward
         if exact_hidden:
             hidden = F.linear(x, weight, bias)
             if gate_w is not None:
-                gate_pre = ops.gemm_nt([x], gate_w.t().contiguous(), gate_b)
+                gate_pre, sp = ops.gemm_nt([x], gate_w.t().contiguous(), gate_b, return_splits=True)
+                x_split = sp[0]
         elif gate_w is None:
-            hidden = ops.gemm_nt([x], weight, bias)
+            hidden, sp = ops.gemm_nt([x], weight, bias, return_splits=True)
+            x_split = sp[0]
         else:
             b0 = bias if bias is not None else torch.zeros(n_out, device=x.device)
-            hidden, gate_pre = ops.gemm_nt([x], torch.cat([weight, gate_w.t()], 0), torch.cat([b0, gate_b]), n1=n_out)
-        ctx.save_for_backward(x, weight, gate_w if gate_w is not None else weight.new_empty(0))
+            (hidden, gate_pre), sp = ops.gemm_nt([x], torch.cat([weight, gate_w.t()], 0), torch.cat([b0, gate_b]),
+                                                 n1=n_out, return_splits=True)
+            x_split = sp[0]
+        keep_split = USE_TCGEN05_DW and x_split is not None and ctx.needs_input_grad[1]
+        empty = weight.new_empty(0)
+        ctx.save_for_backward(x, weight, gate_w if gate_w is not None else empty,
+                              x_split[0] if keep_split else empty, x_split[1] if keep_split else empty)
         ctx.has_gate = gate_w is not None
         ctx.has_bias = bias is not None
         return hidden, gate_pre
 
     @staticmethod
     def backward(ctx, d_hidden, d_gate):
-        x, weight, gate_w = ctx.saved_tensors
+        x, weight, gate_w, x_hi, x_lo = ctx.saved_tensors
         dx = dW = db = None
         if d_hidden is None:
             d_hidden = torch.zeros(x.shape[0], weight.shape[0], device=x.device)
+        d_hidden = d_hidden.contiguous()
+        use_tc_dw = USE_TCGEN05_DW and ctx.needs_input_grad[1] and weight.shape[0] % 4 == 0 and x.shape[1] % 4 == 0
+        dh_split = ops.split_tf32(d_hidden, ops._pad16(d_hidden.shape[1])) if (use_tc_dw or ctx.needs_input_grad[0]) else None
         if ctx.needs_input_grad[0]:
             if ctx.has_gate and d_gate is not None:
-                dx = ops.gemm_nt([d_hidden, d_gate], torch.cat([weight.t(), gate_w], 1))
+                dg = d_gate.contiguous()
+                dx = ops.gemm_nt([d_hidden, dg], torch.cat([weight.t(), gate_w], 1),
+                                 a_splits=[dh_split, ops.split_tf32(dg, ops._pad16(dg.shape[1]))])
             else:
-                dx = ops.gemm_nt([d_hidden], weight.t().contiguous())
+                dx = ops.gemm_nt([d_hidden], weight.t().contiguous(), a_splits=[dh_split])
         if ctx.needs_input_grad[1]:
-            dW = _weight_grad(d_hidden.contiguous(), x)
+            if use_tc_dw:
+                if x_hi.numel() == 0:
+                    x_hi, x_lo = ops.split_tf32(x.contiguous(), ops._pad16(x.shape[1]))
+                dW = ops.gemm_tn(dh_split, weight.shape[0], (x_hi, x_lo), x.shape[1])
+            else:
+                dW = _weight_grad(d_hidden, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = d_hidden.sum(0)
         return dx, dW, db, None, None, None

@@ -355,10 +355,28 @@ def _pad16(k):
     return (k + 15) // 16 * 16
 
 
-def gemm_nt(A_parts, B, bias=None, n1=None):
+def gemm_tn(a_split, m, b_split, n):
+    """C[m, n] = sum_k A[k, m] B[k, n] with fp32 accuracy (3xTF32 on tcgen05, split-K, deterministic).
+    a_split / b_split: (hi, lo) pairs from split_tf32 of the row-major [K, m] / [K, n] operands."""
+    (a_hi, a_lo), (b_hi, b_lo) = a_split, b_split
+    K = a_hi.shape[0]
+    if b_hi.shape[0] != K:
+        raise ValueError("gemm_tn: operands disagree on the reduction length")
+    dev = a_hi.device
+    out = torch.empty(m, n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nb = int(lib.eg_gemm_tn_3xtf32_workspace_bytes(K, m, n))
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        check(lib.eg_gemm_tn_3xtf32(ptr(a_hi), ptr(a_lo), m, a_hi.shape[1], ptr(b_hi), ptr(b_lo), n, b_hi.shape[1], K,
+                                    ptr(ws), nb, ptr(out), n, stream()), "eg_gemm_tn_3xtf32")
+    return out
+
+
+def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False):
     """C = [A1 | A2 ...] · Bᵀ + bias with fp32 accuracy (3xTF32 on tcgen05).
     A_parts: one or two [m, k_i] fp32 CUDA tensors; B: [n, sum k_i] fp32 (row j = output column j).
-    Returns out1 [m, n1] (and out2 [m, n - n1] when n1 < n)."""
+    Returns out1 [m, n1] (and out2 [m, n - n1] when n1 < n).  ``a_splits``: reuse hi/lo pairs computed earlier
+    (one per A part, padded to 16 columns); ``return_splits=True`` appends the list of pairs used."""
     A_parts = [_f32c(a) for a in A_parts]
     if not 1 <= len(A_parts) <= 2:
         raise ValueError("gemm_nt takes one or two A operands")
@@ -370,7 +388,7 @@ def gemm_nt(A_parts, B, bias=None, n1=None):
         raise ValueError("gemm_nt: B has %d columns, A parts have %s" % (B.shape[1], ks))
     n1 = n if n1 is None else n1
     dev = B.device
-    splits = [split_tf32(a, _pad16(a.shape[1])) for a in A_parts]
+    splits = a_splits if a_splits is not None else [split_tf32(a, _pad16(a.shape[1])) for a in A_parts]
     # B's K axis is laid out part by part, each padded to 16, to match the k-blocks of the A parts
     if len(ks) == 1 and ks[0] % 16 == 0:
         Bp = B
@@ -391,7 +409,8 @@ def gemm_nt(A_parts, B, bias=None, n1=None):
                                     _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
                                     ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
               "eg_gemm_nt_3xtf32")
-    return (out1, out2) if out2 is not None else out1
+    res = (out1, out2) if out2 is not None else out1
+    return (res, splits) if return_splits else res
 
 
 # ---- margin ranking loss (fused gather + L1 + hinge) --------------------------------------------

@@ -213,6 +213,16 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
                       const float* B_hi, const float* B_lo, int64_t n, const float* bias,
                       float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
 
+/* Weight gradient of those products: C[m, n] = sum_k A[k, m] * B[k, n]  (dW = dH^T x; K = #entities).
+ * A, B are the SAME row-major hi/lo split arrays ([K, lda], [K, ldb], lda/ldb % 4 == 0, 16-byte aligned) that
+ * eg_gemm_nt_3xtf32 consumes — the tensor cores read them as MN-major operands, no transposed copy.  Split-K
+ * over the grid; ws holds the per-split partial tiles (eg_gemm_tn_3xtf32_workspace_bytes), summed in split
+ * order (deterministic). */
+size_t eg_gemm_tn_3xtf32_workspace_bytes(int64_t K, int m, int n);
+int eg_gemm_tn_3xtf32(const float* A_hi, const float* A_lo, int m, int lda,
+                      const float* B_hi, const float* B_lo, int n, int ldb, int64_t K,
+                      void* ws, size_t ws_bytes, float* out, int64_t ldo, eg_stream_t stream);
+
 /* ---- margin-based L1 ranking loss with hard negatives -------------
  * Replaces the four [t*k, d] gathers + abs/sum/relu of models/models_ea.py:103-123,185-204:
  *   *loss_sum = sum_{p<t, q<k} relu(A_p + gamma - |out[nl]-out[nr]|_1) + relu(A_p + gamma - |out[n2l]-out[n2r]|_1),

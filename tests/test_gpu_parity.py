@@ -633,3 +633,21 @@ def test_gat_encoder_trains(dev):
     hcur.square().sum().backward()
     assert relerr(y, hcur.detach()) < REL
     assert relerr(x.grad, xc.grad) < 5e-4
+
+
+@pytest.mark.parametrize("K,m,n", [(1, 4, 4), (37, 300, 300), (5000, 300, 300), (20011, 128, 160), (3333, 20, 516),
+                                   (200000, 300, 300)])
+def test_gemm_tn_3xtf32_matches_fp64(K, m, n, dev):
+    """dW-shaped product sum_k A[k, m] B[k, n] on the MN-major split-K tcgen05 kernel against fp64; ragged K, tile
+    edges, one and many K splits; bit-identical across repeats (fixed-order split reduction)."""
+    from gnn_mtl_b200 import ops
+    gen = torch.Generator().manual_seed(K + m)
+    A = torch.randn(K, m, generator=gen)
+    B = torch.randn(K, n, generator=gen)
+    want = A.double().t() @ B.double()
+    Ag, Bg = A.to(dev), B.to(dev)
+    sa, sb = ops.split_tf32(Ag, ops._pad16(m)), ops.split_tf32(Bg, ops._pad16(n))
+    got = ops.gemm_tn(sa, m, sb, n)
+    scale = float(want.abs().max())
+    assert float((got.double().cpu() - want).abs().max()) < 2e-6 * max(scale, 1.0) * max(1.0, (K / 1000.0) ** 0.5)
+    assert torch.equal(got, ops.gemm_tn(sa, m, sb, n))
