@@ -132,6 +132,11 @@ class _DenseProducts(torch.autograd.Function):
                                                  n1=n_out, return_splits=True)
             x_split = sp[0]
         keep_split = USE_TCGEN05_DW and x_split is not None and ctx.needs_input_grad[1]
+        # db = dHᵀ·1 rides along with dW = dHᵀ·x: the first padding column of x's hi part is set to one (the
+        # forward products above are done with it; their weight operand is zero over the padding)
+        ctx.ones_col = bool(keep_split and bias is not None and x_split[0].shape[1] > x.shape[1])
+        if ctx.ones_col:
+            x_split[0][:, x.shape[1]] = 1.0
         empty = weight.new_empty(0)
         ctx.save_for_backward(x, weight, gate_w if gate_w is not None else empty,
                               x_split[0] if keep_split else empty, x_split[1] if keep_split else empty)
@@ -159,10 +164,14 @@ class _DenseProducts(torch.autograd.Function):
             if use_tc_dw:
                 if x_hi.numel() == 0:
                     x_hi, x_lo = ops.split_tf32(x.contiguous(), ops._pad16(x.shape[1]))
-                dW = ops.gemm_tn(dh_split, weight.shape[0], (x_hi, x_lo), x.shape[1])
+                if ctx.ones_col and ctx.needs_input_grad[2]:
+                    both = ops.gemm_tn(dh_split, weight.shape[0], (x_hi, x_lo), x.shape[1] + 1)
+                    dW, db = both[:, :x.shape[1]].contiguous(), both[:, x.shape[1]].contiguous()
+                else:
+                    dW = ops.gemm_tn(dh_split, weight.shape[0], (x_hi, x_lo), x.shape[1])
             else:
                 dW = _weight_grad(d_hidden, x)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if db is None and ctx.has_bias and ctx.needs_input_grad[2]:
             db = d_hidden.sum(0)
         return dx, dW, db, None, None, None
 
