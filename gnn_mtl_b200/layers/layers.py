@@ -119,7 +119,11 @@ class _DenseProducts(torch.autograd.Function):
         gate_pre = None
         x_split = None                      # hi/lo split of x: made once, reused by dW = dHᵀ·x in backward
         if exact_hidden:
-            hidden = F.linear(x, weight, bias)
+            # cuBLAS fp32; the bias is added in place afterwards (cublasLt's own bias pass for this shape is a
+            # separate 0.34 ms kernel, the in-place add 0.16 ms; same roundings: fl(fl(x·Wᵀ) + b))
+            hidden = torch.mm(x, weight.t())
+            if bias is not None:
+                hidden.add_(bias)
             if gate_w is not None:
                 gate_pre, sp = ops.gemm_nt([x], gate_w.t().contiguous(), gate_b, return_splits=True)
                 x_split = sp[0]
