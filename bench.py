@@ -358,6 +358,11 @@ def run_ours(args):
                             "formulation. What binds it instead: two grid barriers (~1.2 us each) and two L2 round "
                             "trips per sweep; the mat-vec phases themselves take ~1 us each (EG_PERSIST_TIMING=1)."}
     roofline_dom["frac"] = roofline_dom["achieved"] / roofline_dom["peak"]
+    try:    # how often the scaling-domain solve had to be redone in the log domain during this run (0 expected)
+        from gnn_mtl_b200 import _lib as _eg
+        roofline_dom["log_domain_redos_in_run"] = int(_eg.lib.eg_debug_set(8, 0))
+    except Exception:
+        pass
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "sinkhorn_onchip_traffic.json")))
         roofline_dom["traffic"] = tj.get("dram_bytes_per_launch")
