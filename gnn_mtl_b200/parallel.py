@@ -77,6 +77,46 @@ def allreduce_grads(params, group=None):
         off += n
 
 
+def column_chunks(d, n_chunks, align=4):
+    """Split [0, d) into at most n_chunks contiguous ranges whose starts are multiples of `align`."""
+    per = -(-d // max(n_chunks, 1))
+    per = -(-per // align) * align
+    return [(c0, min(d, c0 + per)) for c0 in range(0, d, per)]
+
+
+def gather_apply_overlapped(local_rows, n_total, apply_fn, n_chunks=4, group=None, align=4):
+    """out = apply_fn(all-gathered rows), pipelined over column chunks: while apply_fn works on the gathered
+    columns of chunk c (on the current stream) the all-gather of chunk c+1 is already in flight on a side stream.
+    apply_fn must act column-wise (out[:, j] depends on input[:, j] only — an SpMM does), so the result is
+    bit-identical to the unchunked call.  Returns cat of the per-chunk outputs along dim 1."""
+    rank, size = world(group)
+    d = local_rows.shape[1]
+    chunks = column_chunks(d, n_chunks, align)
+    if size == 1 or len(chunks) <= 1:
+        return apply_fn(all_gather_rows(local_rows, n_total, group))
+    if not local_rows.is_cuda:                       # gloo / CPU: same schedule, no streams
+        return torch.cat([apply_fn(all_gather_rows(local_rows[:, c0:c1].contiguous(), n_total, group))
+                          for c0, c1 in chunks], dim=1)
+    cur = torch.cuda.current_stream(local_rows.device)
+    side = torch.cuda.Stream(device=local_rows.device)
+    side.wait_stream(cur)
+    gathered, ready = [], []
+    with torch.cuda.stream(side):
+        for c0, c1 in chunks:
+            g = all_gather_rows(local_rows[:, c0:c1].contiguous(), n_total, group)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            gathered.append(g)
+            ready.append(ev)
+    local_rows.record_stream(side)
+    outs = []
+    for g, ev in zip(gathered, ready):
+        cur.wait_event(ev)
+        g.record_stream(cur)
+        outs.append(apply_fn(g))
+    return torch.cat(outs, dim=1)
+
+
 # --------------------------------------------------------------------------- Sinkhorn
 
 def sharded_sinkhorn(col_lse_local, row_update_local, n_rows_total, n_cols, log_b, b, n_local, device, dtype,
@@ -197,3 +237,9 @@ class ShardedAdjacency:
 
     def local(self, full_rows):
         return full_rows[self.r0:self.r1]
+
+    def aggregate_overlapped(self, local_rows, transposed=False, n_chunks=4):
+        """(A or Aᵀ)[my rows] · H with the feature all-gather pipelined against the SpMM over column chunks."""
+        from . import ops
+        csr = self.csr_t if transposed else self.csr
+        return gather_apply_overlapped(local_rows, self.n, lambda g: ops.spmm(csr, g)[0], n_chunks, self.group)

@@ -60,6 +60,13 @@ def main():
     assert float((y_loc - y_full[sh.r0:sh.r1]).abs().max()) < 1e-5
     assert float((xl.grad - xf.grad[sh.r0:sh.r1]).abs().max()) < 1e-5
     assert float((gWl - gW).abs().max() / gW.abs().max()) < 1e-4
+    # ---- (d) all-gather pipelined against the SpMM over column chunks: bit-identical to gather-then-SpMM ----
+    from gnn_mtl_b200 import ops
+    Hl = x[sh.r0:sh.r1].contiguous()
+    plain = ops.spmm(sh.csr, sh.gather(Hl))[0]
+    for chunks in (2, 4, 5):
+        assert torch.equal(sh.aggregate_overlapped(Hl, n_chunks=chunks), plain)
+    assert torch.equal(sh.aggregate_overlapped(Hl, transposed=True), ops.spmm(sh.csr_t, sh.gather(Hl))[0])
     dist.barrier()
     if rank == 0:
         print("mgpu_check ok: world %d | sinkhorn du %.1e dv %.1e dloss %.1e" % (world, e_u, e_v, e_l))

@@ -145,6 +145,30 @@ def _w_sharded_adjacency(rank, world):
         assert int(c.seg_begin.min()) >= 0 and int(c.seg_end.max()) <= c.nnz
 
 
-@pytest.mark.parametrize("worker", [_w_sinkhorn, _w_gather_and_grads, _w_rank_merge, _w_sharded_adjacency])
+def _w_overlapped_gather(rank, world):
+    """Column-chunked gather + column-wise operator == unchunked call, bit for bit; chunk bounds aligned."""
+    from gnn_mtl_b200 import parallel as par
+    assert par.column_chunks(300, 4) == [(0, 76), (76, 152), (152, 228), (228, 300)]
+    assert par.column_chunks(7, 4, align=4) == [(0, 4), (4, 7)]
+    assert par.column_chunks(8, 1) == [(0, 8)]
+    g = torch.Generator().manual_seed(0)
+    n, d = 37, 22
+    H = torch.randn(n, d, generator=g)
+    M = torch.randn(11, n, generator=g)
+    r0, r1 = par.shard_range(n, rank, world)
+    calls = []
+
+    def op(full_rows):
+        calls.append(full_rows.shape[1])
+        return M @ full_rows
+    got = par.gather_apply_overlapped(H[r0:r1], n, op, n_chunks=3)
+    assert calls == [8, 8, 6]
+    want = torch.cat([M @ H[:, c0:c1] for c0, c1 in par.column_chunks(d, 3)], 1)
+    assert torch.equal(got, want)
+    assert torch.allclose(got, M @ H, atol=1e-5)
+
+
+@pytest.mark.parametrize("worker", [_w_sinkhorn, _w_gather_and_grads, _w_rank_merge, _w_sharded_adjacency,
+                                    _w_overlapped_gather])
 def test_world2_gloo(worker):
     _run(worker, 2)

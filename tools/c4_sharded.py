@@ -27,8 +27,12 @@ for d in (128, 300):
         return ops.spmm(sh.csr_t if sh else full.csr_t, Hf)[0]
     def gather_only():
         return sh.gather(H_local) if sh else H_local
+    def fwd_overlap():
+        return sh.aggregate_overlapped(H_local, n_chunks=4) if sh else fwd()
+    if sh:
+        assert torch.equal(fwd_overlap(), fwd())          # column chunks do not change a single bit
     out = {}
-    for name, f in (("fwd", fwd), ("bwd", bwd), ("allgather", gather_only)):
+    for name, f in (("fwd", fwd), ("bwd", bwd), ("allgather", gather_only), ("fwd_overlap", fwd_overlap)):
         for _ in range(2): f()
         torch.cuda.synchronize()
         if world > 1: dist.barrier()
@@ -41,6 +45,7 @@ for d in (128, 300):
         out[name] = float(ms[0])
     byt = nnz * 8 + (n + 1) * 4 + nnz * d * 4 + n * d * 4
     res.append({"d": d, "fwd_ms": out["fwd"], "bwd_ms": out["bwd"], "allgather_ms": out["allgather"],
+                "fwd_overlap_ms": out["fwd_overlap"], "fwd_overlap_gbs_aggregate": byt / out["fwd_overlap"] / 1e6,
                 "fwd_gbs_aggregate": byt / out["fwd"] / 1e6, "bwd_gbs_aggregate": byt / out["bwd"] / 1e6,
                 "spmm_only_gbs_aggregate": byt / max(out["fwd"] - out["allgather"], 1e-6) / 1e6})
 if rank == 0:
