@@ -88,7 +88,11 @@ def gather_apply_overlapped(local_rows, n_total, apply_fn, n_chunks=4, group=Non
     """out = apply_fn(all-gathered rows), pipelined over column chunks: while apply_fn works on the gathered
     columns of chunk c (on the current stream) the all-gather of chunk c+1 is already in flight on a side stream.
     apply_fn must act column-wise (out[:, j] depends on input[:, j] only — an SpMM does), so the result is
-    bit-identical to the unchunked call.  Returns cat of the per-chunk outputs along dim 1."""
+    bit-identical to the unchunked call.  Returns cat of the per-chunk outputs along dim 1.
+
+    Measured on 2 B200s (profiles/r01_multi_gpu.md) this LOSES for the SpMM: narrow column chunks cost the gather
+    kernel more than the overlap saves, so nothing calls it by default; kept as the tested building block for
+    operators whose cost does not depend on the row width."""
     rank, size = world(group)
     d = local_rows.shape[1]
     chunks = column_chunks(d, n_chunks, align)
