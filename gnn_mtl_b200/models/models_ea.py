@@ -8,7 +8,6 @@ from __future__ import annotations
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 from ..utils.eval_utils import get_hits

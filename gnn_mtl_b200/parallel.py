@@ -193,7 +193,6 @@ def merge_rank_counts(rank_row_local, rank_col_partial, n_total, group=None):
 def get_hits_sharded(vec, test_pair, top_k=(1, 10, 50, 100), group=None):
     """utils/eval_utils.py:71-98 with the rows of the L1 matrix split over ranks.
     Every rank passes the same `vec` / `test_pair` and gets the same dict."""
-    import numpy as np
     from . import ops
     from .utils.eval_utils import _hits_dict, _pair_index, _to_cuda
     rank, size = world(group)

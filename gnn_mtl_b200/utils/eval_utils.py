@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .. import _lib, ops
+from .. import ops
 
 
 def format_metrics(metrics, split):
