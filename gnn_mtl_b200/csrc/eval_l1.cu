@@ -78,20 +78,79 @@ __device__ __forceinline__ void l1_tile_accumulate(const float* __restrict__ L, 
   }
 }
 
-__global__ void __launch_bounds__(256, 2)
+// Same tile with an 8 x 4 register block per thread and 128 threads: thread (ty = tid >> 4, tx = tid & 15) owns
+// rows i0 + 8*ty .. +7 and the same four columns as above.  An LDS.128 costs four shared-memory wavefronts per
+// warp whether or not lanes share addresses, so the 4 x 4 block (4 LDS.128 per 32 DADD) keeps the shared-memory
+// pipe ~83 % busy at full FP64 rate (profiles/README.md); 8 x 4 needs 6 LDS.128 per 64 DADD.
+constexpr int kKC8 = 16;     // k-chunk of the 8 x 4 variant (prefetch registers: 2 x 8 per thread)
+
+__device__ __forceinline__ void l1_tile_accumulate8(const float* __restrict__ L, int64_t nL,
+                                                    const float* __restrict__ R, int64_t nR, int d, int64_t i0,
+                                                    int64_t j0, double (*Ls)[kPad], double (*Rs)[kPad],
+                                                    double (&acc)[8][4]) {
+  const int tx = threadIdx.x & 15;
+  const int ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  // staging: thread t owns element (row = t / 16 + 8*r, k = t % 16) of both tiles
+  const int kk = threadIdx.x & 15;
+  const int rbase = threadIdx.x >> 4;
+  float lreg[kTile / 8], rreg[kTile / 8];
+  auto fetch = [&](int k0) {
+    const int kc = min(kKC8, d - k0);
+#pragma unroll
+    for (int r = 0; r < kTile / 8; ++r) {
+      const int row = rbase + 8 * r;
+      lreg[r] = (kk < kc && i0 + row < nL) ? __ldg(L + (i0 + row) * d + k0 + kk) : 0.f;
+      rreg[r] = (kk < kc && j0 + row < nR) ? __ldg(R + (j0 + row) * d + k0 + kk) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < d; k0 += kKC8) {
+    const int kc = min(kKC8, d - k0);
+#pragma unroll
+    for (int r = 0; r < kTile / 8; ++r) {
+      Ls[kk][rbase + 8 * r] = (double)lreg[r];
+      Rs[kk][rbase + 8 * r] = (double)rreg[r];
+    }
+    __syncthreads();
+    if (k0 + kKC8 < d) fetch(k0 + kKC8);
+#pragma unroll 4
+    for (int k = 0; k < kc; ++k) {
+      double lv[8], rv[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const double2 l2 = *reinterpret_cast<const double2*>(&Ls[k][8 * ty + 2 * h]);
+        lv[2 * h] = l2.x; lv[2 * h + 1] = l2.y;
+      }
+      const double2 r01 = *reinterpret_cast<const double2*>(&Rs[k][2 * tx]);
+      const double2 r23 = *reinterpret_cast<const double2*>(&Rs[k][32 + 2 * tx]);
+      rv[0] = r01.x; rv[1] = r01.y; rv[2] = r23.x; rv[3] = r23.y;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = __dadd_rn(acc[a][b], fabs(__dsub_rn(lv[a], rv[b])));
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128, 3)
 l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict__ R, int64_t nR, int d,
                double* __restrict__ D, int64_t ldD) {
-  __shared__ __align__(16) double Ls[kKC][kPad];
-  __shared__ __align__(16) double Rs[kKC][kPad];
+  __shared__ __align__(16) double Ls[kKC8][kPad];
+  __shared__ __align__(16) double Rs[kKC8][kPad];
   const int tx = threadIdx.x & 15;
   const int ty = threadIdx.x >> 4;
   const int64_t i0 = (int64_t)blockIdx.y * kTile;
   const int64_t j0 = (int64_t)blockIdx.x * kTile;
-  double acc[4][4];
-  l1_tile_accumulate(L, nL, R, nR, d, i0, j0, Ls, Rs, acc);
+  double acc[8][4];
+  l1_tile_accumulate8(L, nL, R, nR, d, i0, j0, Ls, Rs, acc);
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    int64_t i = i0 + 4 * ty + a;
+  for (int a = 0; a < 8; ++a) {
+    int64_t i = i0 + 8 * ty + a;
     if (i >= nL) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -111,12 +170,12 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
 // A CTA owns a 64-row strip and walks `tiles_per_cta` consecutive column tiles.
 
 // Rank counts of eg_rank_accumulate, taken straight from the accumulators.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(128, 3)
 l1_rank_fused_kernel(const float* __restrict__ L, int64_t nL, int64_t row0, const float* __restrict__ R, int64_t nR,
                      int d, int tiles_per_cta, const double* __restrict__ diag, int32_t* __restrict__ rank_row,
                      int32_t* __restrict__ rank_col) {
-  __shared__ __align__(16) double Ls[kKC][kPad];
-  __shared__ __align__(16) double Rs[kKC][kPad];
+  __shared__ __align__(16) double Ls[kKC8][kPad];
+  __shared__ __align__(16) double Rs[kKC8][kPad];
   __shared__ int col_cnt_s[2][kTile];
   const int tx = threadIdx.x & 15;
   const int ty = threadIdx.x >> 4;
@@ -124,22 +183,23 @@ l1_rank_fused_kernel(const float* __restrict__ L, int64_t nL, int64_t row0, cons
   const int64_t n_col_tiles = (nR + kTile - 1) / kTile;
   const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
   const int64_t t_end = min(n_col_tiles, t_begin + tiles_per_cta);
-  double di[4];
-  int64_t gi[4];
-  int row_cnt[4] = {0, 0, 0, 0};
+  double di[8];
+  int64_t gi[8];
+  int row_cnt[8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int64_t i = i0 + 4 * ty + a;
+  for (int a = 0; a < 8; ++a) {
+    const int64_t i = i0 + 8 * ty + a;
     gi[a] = row0 + i;                              // global row id == index of its true match
     di[a] = (i < nL) ? diag[gi[a]] : 0.0;
+    row_cnt[a] = 0;
   }
-  if (threadIdx.x < 2 * kTile) (&col_cnt_s[0][0])[threadIdx.x] = 0;
+  (&col_cnt_s[0][0])[threadIdx.x] = 0;             // 128 threads == 2 * kTile entries
   __syncthreads();
   int buf = 0;
   for (int64_t t = t_begin; t < t_end; ++t, buf ^= 1) {
     const int64_t j0 = t * kTile;
-    double acc[4][4];
-    l1_tile_accumulate(L, nL, R, nR, d, i0, j0, Ls, Rs, acc);
+    double acc[8][4];
+    l1_tile_accumulate8(L, nL, R, nR, d, i0, j0, Ls, Rs, acc);
     int col_cnt[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -147,8 +207,8 @@ l1_rank_fused_kernel(const float* __restrict__ L, int64_t nL, int64_t row0, cons
       const bool col_ok = j < nR;
       const double dj = col_ok ? __ldg(diag + j) : 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const bool ok = col_ok && (i0 + 4 * ty + a < nL);
+      for (int a = 0; a < 8; ++a) {
+        const bool ok = col_ok && (i0 + 8 * ty + a < nL);
         const double v = acc[a][b];
         row_cnt[a] += ok && ((v < di[a]) || (v == di[a] && j < gi[a]));
         col_cnt[b] += ok && ((v < dj) || (v == dj && gi[a] < j));
@@ -164,15 +224,15 @@ l1_rank_fused_kernel(const float* __restrict__ L, int64_t nL, int64_t row0, cons
       const int c = col_cnt_s[buf][threadIdx.x];
       if (c) { atomicAdd(&rank_col[j0 + threadIdx.x], c); col_cnt_s[buf][threadIdx.x] = 0; }
     }
-    // no second barrier: the next tile adds into the other buffer, and l1_tile_accumulate's own barriers
+    // no second barrier: the next tile adds into the other buffer, and l1_tile_accumulate8's own barriers
     // order this buffer's reset before its reuse two tiles later
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
+  for (int a = 0; a < 8; ++a) {
     int c = row_cnt[a];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (tx == 0 && c && i0 + 4 * ty + a < nL) atomicAdd(&rank_row[gi[a]], c);
+    if (tx == 0 && c && i0 + 8 * ty + a < nL) atomicAdd(&rank_row[gi[a]], c);
   }
 }
 
@@ -587,7 +647,7 @@ int eg_l1_rank_fused(const float* L, int64_t nL, int64_t row0, const float* R, i
   cudaStream_t s = as_stream(stream_);
   EG_CUDA(cudaMemsetAsync(rank_row + row0, 0, sizeof(int32_t) * (size_t)nL, s));
   dim3 grid((unsigned)n_seg, (unsigned)gy);
-  l1_rank_fused_kernel<<<grid, 256, 0, s>>>(L, nL, row0, R, nR, d, per, diag, rank_row, rank_col);
+  l1_rank_fused_kernel<<<grid, 128, 0, s>>>(L, nL, row0, R, nR, d, per, diag, rank_row, rank_col);
   EG_LAUNCHED();
   return EG_OK;
 }
@@ -640,7 +700,7 @@ int eg_l1_matrix(const float* L, int64_t nL, const float* R, int64_t nR, int d, 
   int64_t gy = ceil_div(nL, kTile);
   if (gy > 65535) return EG_ERR_UNSUPPORTED;  // callers block rows (<= 4M rows per call)
   dim3 grid((unsigned)ceil_div(nR, kTile), (unsigned)gy);
-  l1_tile_kernel<<<grid, 256, 0, as_stream(stream_)>>>(L, nL, R, nR, d, D, ldD);
+  l1_tile_kernel<<<grid, 128, 0, as_stream(stream_)>>>(L, nL, R, nR, d, D, ldD);
   EG_LAUNCHED();
   return EG_OK;
 }
