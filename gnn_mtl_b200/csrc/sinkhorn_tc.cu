@@ -94,6 +94,7 @@ __device__ __forceinline__ float exact_pair_warp(const float* __restrict__ a, co
 }
 
 struct Params {
+  int bn;                 // MODE 2: columns per tile (multiple of 16, <= BN), chosen so that padding is small
   int64_t nA, nB;
   int k_blocks;            // ceil(d_pad / BK)
   int d_pad;               // operand row length (multiple of 8)
@@ -139,10 +140,20 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.x * BM;
-  const int n_btiles = (int)((p.nB + BN - 1) / BN);
+  const int bn = (MODE == 2) ? p.bn : BN;                 // UMMA N of this launch
+  const int n_btiles = (int)((p.nB + bn - 1) / bn);
   const int t_begin = blockIdx.y * p.tiles_per_split;
   const int t_end = min(n_btiles, t_begin + p.tiles_per_split);
-  const int n_tiles = max(t_end - t_begin, 0);
+  // MODE 0/1: this CTA owns one row tile and walks its column tiles.  MODE 2 (GEMM) is persistent: the CTA walks
+  // row tiles blockIdx.x, blockIdx.x + gridDim.x, ... and all column tiles of each, as one continuous pipeline
+  // (a 3-tile CTA spent a third of its life in prologue and the un-overlapped last epilogue).
+  const int n_rtiles = (int)((p.nA + BM - 1) / BM);
+  const int my_rtiles = (MODE == 2) ? (n_rtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  const int n_tiles = (MODE == 2) ? my_rtiles * n_btiles : max(t_end - t_begin, 0);
+  auto tile_i0 = [&](int t) -> int64_t {
+    return (MODE == 2) ? ((int64_t)blockIdx.x + (int64_t)(t / n_btiles) * gridDim.x) * BM : i0;
+  };
+  auto tile_j0 = [&](int t) -> int { return (MODE == 2) ? (t % n_btiles) * bn : (t_begin + t) * BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -164,17 +175,18 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int j0 = (t_begin + t) * BN;
+        const int j0 = tile_j0(t);
+        const int ti0 = (int)tile_i0(t);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = stage_base + s * STAGE_BYTES;
-          mbar_expect_tx(&full[s], STAGE_BYTES);
+          mbar_expect_tx(&full[s], 2 * A_TILE_BYTES + 2 * bn * BK * 4);   // the B boxes are bn rows tall
           if (MODE != 2 || kb < p.kb_split) {
-            tma_load_2d(st, &map_a_hi, &full[s], kb * BK, (int)i0);
-            tma_load_2d(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, (int)i0);
+            tma_load_2d(st, &map_a_hi, &full[s], kb * BK, ti0);
+            tma_load_2d(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, ti0);
           } else {
-            tma_load_2d(st, &map_a2_hi, &full[s], (kb - p.kb_split) * BK, (int)i0);
-            tma_load_2d(st + A_TILE_BYTES, &map_a2_lo, &full[s], (kb - p.kb_split) * BK, (int)i0);
+            tma_load_2d(st, &map_a2_hi, &full[s], (kb - p.kb_split) * BK, ti0);
+            tma_load_2d(st + A_TILE_BYTES, &map_a2_lo, &full[s], (kb - p.kb_split) * BK, ti0);
           }
           tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full[s], kb * BK, j0);
           tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[s], kb * BK, j0);
@@ -185,7 +197,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, bn);
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
@@ -230,7 +242,8 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     double loss_acc = 0.0;
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
-      const int64_t j0 = (int64_t)(t_begin + t) * BN;
+      const int64_t j0 = tile_j0(t);
+      const int64_t trow = tile_i0(t) + row_in_tile;        // == row except in the persistent GEMM mode
       // stage (norm_b, pot_b) for this tile; buffer `buf` was last read two tiles ago
       float2* ci = colinfo + buf * BN;
       for (int c = ep_tid; c < BN; c += 128) {
@@ -245,18 +258,18 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < bn; c0 += 32) {
         float dot[32];
         tmem_ld32(taddr + (uint32_t)c0, dot);
         if (MODE == 2) {
-          if (row < p.nA) {
+          if (trow < p.nA) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
               const int64_t j = j0 + c0 + c;
-              if (j < p.nB) {      // nB, n1 are multiples of 4 (checked on the host)
+              if (j < p.nB && c0 + c < bn) {      // nB, n1, bn are multiples of 4 (checked on the host)
                 const float4 v = make_float4(dot[c] + ci[c0 + c].y, dot[c + 1] + ci[c0 + c + 1].y,
                                              dot[c + 2] + ci[c0 + c + 2].y, dot[c + 3] + ci[c0 + c + 3].y);
-                float* dst = (j < p.n1) ? p.out1 + row * p.ld1 + j : p.out2 + row * p.ld2 + (j - p.n1);
+                float* dst = (j < p.n1) ? p.out1 + trow * p.ld1 + j : p.out2 + trow * p.ld2 + (j - p.n1);
                 *reinterpret_cast<float4*>(dst) = v;
               }
             }
@@ -537,19 +550,23 @@ int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_
     L.ma2_hi = L.ma_hi;
     L.ma2_lo = L.ma_lo;
   }
-  if ((rc = make_map(&L.mb_hi, B_hi, n, kp, BN))) return rc;
-  if ((rc = make_map(&L.mb_lo, B_lo, n, kp, BN))) return rc;
+  // column tile: as few tiles as BN = 256 allows, each just wide enough (multiple of 16): n = 300 -> 2 x 160, not 2 x 256
+  const int64_t n_ct = ceil_div(n, (int64_t)BN);
+  const int bn = (int)std::min<int64_t>(BN, ceil_div(ceil_div(n, n_ct), (int64_t)16) * 16);
+  if ((rc = make_map(&L.mb_hi, B_hi, n, kp, bn))) return rc;
+  if ((rc = make_map(&L.mb_lo, B_lo, n, kp, bn))) return rc;
   Params& p = L.p;
   p = Params{};
   p.nA = m; p.nB = n; p.k_blocks = kp / BK; p.d_pad = kp; p.kb_split = k1p / BK;
   p.pot_in = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
-  p.tiles_per_split = (int)ceil_div(n, BN);
+  p.bn = bn;
+  p.tiles_per_split = (int)ceil_div(n, (int64_t)bn);
   static bool attr_set = false;
   if (!attr_set) {
     EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(m, BM), 1);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(m, BM), kNumSMs), 1);    // persistent over row tiles
   lse_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
   EG_LAUNCHED();
   return EG_OK;
