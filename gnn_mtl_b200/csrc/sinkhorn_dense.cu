@@ -1113,7 +1113,7 @@ sinkhorn_onchip_scaling_kernel(const float* __restrict__ M, int64_t I, int J, in
       // all dot products first (register rows + shared-memory rows 0..23, clamped / zero-selected, so the loads
       // are unconditional and deep in flight), then the four 8-value transposes back to back so their shuffle
       // latencies overlap; rows 24..31 (only when S > 24) go through a separate, uniform-branch batch
-      float pr[8], pb[3][8];
+      float pr[8], pb[2][8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) pr[k] = 0.f;
 #pragma unroll
@@ -1140,27 +1140,34 @@ sinkhorn_onchip_scaling_kernel(const float* __restrict__ M, int64_t I, int J, in
         }
       };
 #pragma unroll
-      for (int batch = 0; batch < 3; ++batch) {
+      for (int batch = 0; batch < 2; ++batch) {
         rows4(batch * 8, pb[batch], 0);
         rows4(batch * 8 + 4, pb[batch], 4);
       }
       const float tr = warp_transpose_sum8(pr, lane);
       const float t0 = warp_transpose_sum8(pb[0], lane);
       const float t1 = warp_transpose_sum8(pb[1], lane);
-      const float t2 = warp_transpose_sum8(pb[2], lane);
       if (lane < 8) {
         red[warp * kScSlots + lane] = tr;
         red[warp * kScSlots + 8 + lane] = t0;
         red[warp * kScSlots + 16 + lane] = t1;
-        red[warp * kScSlots + 24 + lane] = t2;
       }
-      if (S > 24) {
-        rows4(24, pr, 0);
-        rows4(28, pr, 4);
-        const float t3 = warp_transpose_sum8(pr, lane);
-        if (lane < 8) red[warp * kScSlots + 32 + lane] = t3;
-      } else if (lane < 8) {
-        red[warp * kScSlots + 32 + lane] = 0.f;
+      // rows 16..31 in two more batches, each behind a uniform branch (19 rows at J = 3000: one of them, 3 rows live)
+#pragma unroll
+      for (int batch = 2; batch < 4; ++batch) {
+        if (batch * 8 < S) {
+          rows4(batch * 8, pr, 0);
+          if (batch * 8 + 4 < S) {
+            rows4(batch * 8 + 4, pr, 4);
+          } else {
+#pragma unroll
+            for (int k = 4; k < 8; ++k) pr[k] = 0.f;
+          }
+          const float t2 = warp_transpose_sum8(pr, lane);
+          if (lane < 8) red[warp * kScSlots + 8 + batch * 8 + lane] = t2;
+        } else if (lane < 8) {
+          red[warp * kScSlots + 8 + batch * 8 + lane] = 0.f;
+        }
       }
     }
     if (timer) st->t_phase[7] += gtime() - t4;
