@@ -77,8 +77,30 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml_rows, self._stop, self.nvml_thread, self.nvml_error = [], False, None, None
+
+    def _nvml_loop(self):
+        """NVML poll every ~5 ms (nvidia-smi -lms cannot go below ~100 ms; the timed region is ~0.2 s)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._stop:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.nvml_rows.append((float(sm), float(mx), [k for k, b in bits.items() if mask & b]))
+                time.sleep(0.005)
+        except Exception as exc:   # noqa: BLE001 — the nvidia-smi stream below still samples
+            self.nvml_error = "%s: %s" % (type(exc).__name__, exc)
 
     def __enter__(self):
+        self.nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+        self.nvml_thread.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -94,6 +116,7 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self._stop = True
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -104,6 +127,8 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
+        for s_mhz, m_mhz, why in self.nvml_rows:
+            sm.append(s_mhz); mx.append(m_mhz); reasons.update(why)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -115,8 +140,11 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if self.nvml_error:
+            out["nvml_error"] = self.nvml_error
+        return out
 
 
 # --------------------------------------------------------------------------- reference / CPU arm
