@@ -80,7 +80,7 @@ class ClockSampler:
         self.nvml_rows, self._stop, self.nvml_thread, self.nvml_error = [], False, None, None
 
     def _nvml_loop(self):
-        """NVML poll every ~5 ms (nvidia-smi -lms cannot go below ~100 ms; the timed region is ~0.2 s)."""
+        """NVML poll every ~20 ms (nvidia-smi -lms cannot go below ~100 ms; the timed region is ~0.2 s)."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -94,7 +94,7 @@ class ClockSampler:
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.nvml_rows.append((float(sm), float(mx), [k for k, b in bits.items() if mask & b]))
-                time.sleep(0.005)
+                time.sleep(0.02)
         except Exception as exc:   # noqa: BLE001 — the nvidia-smi stream below still samples
             self.nvml_error = "%s: %s" % (type(exc).__name__, exc)
 
