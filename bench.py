@@ -456,7 +456,9 @@ def run_ours(args):
         a_s = torch.full((s1 - s0,), 1.0 / ns, device=dev); b_s = torch.full((ns,), 1.0 / ns, device=dev)
         Xl = Xs[s0:s1].clone()
         del Xs
-        parallel.sinkhorn_fused_sharded(Xl, Ys, a_s, b_s, 0.05, ns, numItermax=1)
+        # two sweeps: the second one runs the marginal-error test, whose torch kernels are otherwise first loaded
+        # (lazy module loading) inside the timed call
+        parallel.sinkhorn_fused_sharded(Xl, Ys, a_s, b_s, 0.05, ns, numItermax=2)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

@@ -21,7 +21,7 @@ if do_eval:
     vec = torch.cat([X, Y])                                 # get_hits takes the stacked embedding table
     pairs = torch.stack([perm, n + torch.arange(n, device=dev)], 1).cpu().numpy()   # Y[j] aligns with X[perm[j]]
 del X
-par.sinkhorn_fused_sharded(Xl, Y, a, b, 0.05, n, numItermax=1)      # warm-up (split, norms, first launches)
+par.sinkhorn_fused_sharded(Xl, Y, a, b, 0.05, n, numItermax=2)      # warm-up incl. the marginal-error test of sweep 1
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
