@@ -78,24 +78,34 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
         self.nvml_rows, self._stop, self.nvml_thread, self.nvml_error = [], False, None, None
+        self._nvml_open()
 
-    def _nvml_loop(self):
-        """NVML poll every ~20 ms (nvidia-smi -lms cannot go below ~100 ms; the timed region is ~0.2 s)."""
+    def _nvml_open(self):
+        """NVML handle, opened before the timed region starts (import + init take tens of ms)."""
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-            while not self._stop:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.nvml_rows.append((float(sm), float(mx), [k for k, b in bits.items() if mask & b]))
-                time.sleep(0.02)
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(self.index)
+            self._mx = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
         except Exception as exc:   # noqa: BLE001 — the nvidia-smi stream below still samples
+            self._nv, self.nvml_error = None, "%s: %s" % (type(exc).__name__, exc)
+
+    def _nvml_loop(self):
+        """NVML poll every ~20 ms (nvidia-smi -lms cannot go below ~100 ms; the timed region is ~0.2 s)."""
+        nv = self._nv
+        if nv is None:
+            return
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        try:
+            while not self._stop:
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.nvml_rows.append((float(sm), self._mx, [k for k, b in bits.items() if mask & b]))
+                time.sleep(0.02)
+        except Exception as exc:   # noqa: BLE001
             self.nvml_error = "%s: %s" % (type(exc).__name__, exc)
 
     def __enter__(self):
