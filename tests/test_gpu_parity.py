@@ -410,7 +410,9 @@ def test_abi_error_behaviour(dev):
         ops.l1_matrix(torch.zeros(2, 2), torch.zeros(2, 2))               # CPU tensors are refused
 
 
-@pytest.mark.parametrize("m,k,n,n1", [(1, 4, 4, 4), (130, 300, 600, 300), (777, 52, 260, 128), (3000, 300, 300, 300)])
+@pytest.mark.parametrize("m,k,n,n1", [(1, 4, 4, 4), (130, 300, 600, 300), (777, 52, 260, 128), (3000, 300, 300, 300),
+                                      (1537, 300, 600, 300), (40001, 300, 300, 300), (20000, 52, 164, 100),
+                                      (5000, 300, 1000, 300)])
 def test_gemm_nt_3xtf32_matches_fp64(m, k, n, n1, dev):
     """layers' dense products on tcgen05: fp32-accurate (3xTF32) against an fp64 reference."""
     from gnn_mtl_b200 import ops
