@@ -99,3 +99,39 @@ def test_dbp15k_loader_host_part_matches_reference(tmp_path, monkeypatch):
     crow, col, val = orc.adjacency_csr(kg["n"], np.array(ref["triple"])[:, 0], np.array(ref["triple"])[:, 2])
     csr = ref["adj"].coalesce().to_sparse_csr()
     assert np.array_equal(csr.crow_indices().numpy(), crow) and np.array_equal(csr.values().numpy(), val)
+
+
+@pytest.mark.parametrize("seed,n_ent,d_in,d_out,alpha", [(0, 120, 16, 12, 0.2), (1, 400, 30, 75, 0.2), (2, 60, 8, 5, 0.01)])
+def test_gat_layer_random_graphs_vs_live_reference(seed, n_ent, d_in, d_out, alpha):
+    """oracle.gat_layer against layers/att_layers.py::SpGraphAttentionLayer on random connected graphs: forward and
+    all three gradients (the golden fixture pins one graph; this widens it where the reference can be imported)."""
+    import warnings
+    import torch.nn.functional as F
+    rng = np.random.default_rng(seed)
+    n_tri = 4 * n_ent
+    h = rng.integers(0, n_ent, n_tri)
+    t = rng.integers(0, n_ent, n_tri)
+    chain = np.arange(n_ent - 1)                       # no isolated entity (the reference asserts on the NaN)
+    h, t = np.concatenate([h, chain]), np.concatenate([t, chain + 1])
+    KG = [(int(a), 0, int(b)) for a, b in zip(h, t)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        du = ref_shim.ref.data_utils
+        adj = du.sparse_mx_to_torch_sparse_tensor(du.get_sparse_tensor(n_ent, KG))
+        att = ref_shim.load("layers.att_layers")
+        torch.manual_seed(seed)
+        layer = att.SpGraphAttentionLayer(d_in, d_out, 0.0, alpha, F.elu)
+        x = torch.randn(n_ent, d_in)
+        xr = x.clone().requires_grad_(True)
+        y_ref = layer(xr, adj)
+        seed_t = torch.randn_like(y_ref)
+        (y_ref * seed_t).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    W = layer.W.detach().clone().requires_grad_(True)
+    a = layer.a.detach().clone().requires_grad_(True)
+    y = orc.gat_layer(xo, orc.adjacency_torch_coo(n_ent, h, t), W, a, alpha, "elu")
+    (y * seed_t).sum().backward()
+    np.testing.assert_allclose(y.detach().numpy(), y_ref.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(xo.grad.numpy(), xr.grad.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(W.grad.numpy(), layer.W.grad.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(a.grad.numpy(), layer.a.grad.numpy(), rtol=2e-4, atol=2e-5)
