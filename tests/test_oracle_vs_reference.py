@@ -135,3 +135,46 @@ def test_gat_layer_random_graphs_vs_live_reference(seed, n_ent, d_in, d_out, alp
     np.testing.assert_allclose(xo.grad.numpy(), xr.grad.numpy(), rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(W.grad.numpy(), layer.W.grad.numpy(), rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(a.grad.numpy(), layer.a.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("seed,n,d,t,k", [(0, 90, 12, 20, 4), (1, 400, 300, 64, 25), (2, 50, 5, 7, 1)])
+def test_margin_loss_random_vs_live_reference(seed, n, d, t, k):
+    """oracle.margin_loss against EAModel.get_loss (models/models_ea.py:103-123): value and gradient."""
+    rng = np.random.default_rng(seed)
+    out = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32) * 0.3).requires_grad_(True)
+    half = n // 2
+    ILL = np.stack([rng.permutation(half)[:t], rng.permutation(half)[:t] + half], 1).astype(np.int64)
+
+    class _Fake:
+        pass
+    me = _Fake()
+    me.neg_num = k
+    me.neg_left = np.repeat(ILL[:, 0], k)
+    me.neg2_right = np.repeat(ILL[:, 1], k)
+    me.neg_right = rng.integers(0, n, t * k)
+    me.neg2_left = rng.integers(0, n, t * k)
+    want = ref_shim.ref.models_ea.EAModel.get_loss(me, out, {"train": ILL}, "train")
+    want.backward()
+    out2 = out.detach().clone().requires_grad_(True)
+    got = orc.margin_loss(out2, ILL, me.neg_left, me.neg_right, me.neg2_left, me.neg2_right, k)
+    got.backward()
+    np.testing.assert_allclose(float(got), float(want), rtol=1e-6)
+    np.testing.assert_allclose(out2.grad.numpy(), out.grad.numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed,I,J,eps,iters", [(0, 30, 40, 0.05, 60), (1, 64, 64, 0.01, 100), (2, 25, 18, 0.002, 40)])
+def test_sinkhorn_iteration_random_vs_live_reference(seed, I, J, eps, iters):
+    """oracle.sinkhorn_stabilised against SinkhornOT.sinkhorn_iteration (sinkhorn_loss.py:159-220), fp64, including
+    a small-epsilon case where the reference's absorption / clamps act."""
+    import contextlib
+    import io
+    rng = np.random.default_rng(seed)
+    C = torch.from_numpy(rng.uniform(size=(1, I, J)))
+    mu = torch.full((1, I, 1), 1.0 / I, dtype=torch.float64)
+    nu = torch.full((1, 1, J), 1.0 / J, dtype=torch.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        w_ref, k1_ref, k2_ref, K_ref = ref_shim.ref.sinkhorn_loss.sinkhorn_iteration(C, mu, nu, eps, numIterMax=iters,
+                                                                                      tol=1e-12, debug=False)
+    w, k1, k2, K = orc.sinkhorn_stabilised(C, mu, nu, eps, numIterMax=iters, tol=1e-12)
+    np.testing.assert_allclose(K.numpy(), K_ref.numpy(), rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(float(w), float(w_ref), rtol=1e-10)
