@@ -178,3 +178,22 @@ def test_sinkhorn_iteration_random_vs_live_reference(seed, I, J, eps, iters):
     w, k1, k2, K = orc.sinkhorn_stabilised(C, mu, nu, eps, numIterMax=iters, tol=1e-12)
     np.testing.assert_allclose(K.numpy(), K_ref.numpy(), rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(float(w), float(w_ref), rtol=1e-10)
+
+
+@pytest.mark.parametrize("seed,I,J,eps,iters", [(0, 14, 19, 0.05, 5), (1, 30, 30, 0.02, 8)])
+def test_gw_projection_random_vs_live_reference(seed, I, J, eps, iters):
+    """oracle.gw_iterative against SinkhornOT.iterative_projection.gw_iterative_1 (:8-60, :119-120), fp64."""
+    import contextlib
+    import io
+    rng = np.random.default_rng(seed)
+    Va = torch.from_numpy(rng.uniform(size=(I, 5)))
+    Vb = torch.from_numpy(rng.uniform(size=(J, 5)))
+    C1 = ref_shim.ref.cderivation.cos_dist_mat(Va, Va).double()
+    C2 = ref_shim.ref.cderivation.cos_dist_mat(Vb, Vb).double()
+    mu = torch.full((I,), 1.0 / I, dtype=torch.float64)
+    nu = torch.full((J,), 1.0 / J, dtype=torch.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        T_ref, gw_ref = ref_shim.ref.iterative_projection.gw_iterative_1(C1, C2, mu, nu, epsilon=eps, max_iter=iters)
+        T, gw = orc.gw_iterative(C1, C2, mu, nu, eps, iters)
+    np.testing.assert_allclose(T.numpy().reshape(I, J), T_ref.numpy().reshape(I, J), rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(float(gw), float(gw_ref), rtol=1e-9)
