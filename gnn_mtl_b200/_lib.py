@@ -30,6 +30,7 @@ SIGNATURES = {
     "eg_device_check": (C.c_int, []),
     "eg_launch_count": (_i64, []),
     "eg_launch_count_reset": (None, []),
+    "eg_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "eg_adj_workspace_bytes": (_sz, [_i64, _i64]),
     "eg_adj_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "eg_csr_transpose_workspace_bytes": (_sz, [_i64, _i64, _i64]),

@@ -39,6 +39,23 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 constexpr int kNumSMs = 148;  // B200
 
+// Function attributes are per device: remember, per kernel call site and device, whether the opt-in dynamic
+// shared-memory size has been set (ops.py serves several devices in one process).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done[4] = {};     // 256 devices
+  bool test(int dev) const { return dev >= 0 && dev < 256 && ((done[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1ull); }
+  void set(int dev) { if (dev >= 0 && dev < 256) done[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+#define EG_SET_SMEM_ONCE(once, ...)                                   \
+  do {                                                                \
+    int _dev = -1;                                                    \
+    EG_CUDA(cudaGetDevice(&_dev));                                    \
+    if (!(once).test(_dev)) {                                         \
+      __VA_ARGS__;                                                    \
+      (once).set(_dev);                                               \
+    }                                                                 \
+  } while (0)
+
 // 128-bit streaming loads/stores: bypass L1 allocation for data touched once.
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;

@@ -16,6 +16,8 @@
 #include "common.cuh"
 
 namespace eg {
+int g_tune_l1_filter = 1;   // eg_debug_set(13, 0): exact fp64 evaluation of every pair (no fp32 candidate filter)
+
 
 constexpr int kTile = 64;     // 64 x 64 distances per CTA
 constexpr int kKC = 32;       // k-chunk staged in shared memory

@@ -276,11 +276,9 @@ int eg_gemm_tn_3xtf32(const float* A_hi, const float* A_lo, int m, int lda, cons
   p.partial = reinterpret_cast<float*>(ws);
   p.ldp = pl.n_tiles * BN;
   p.split_stride = (int64_t)pl.m_tiles * BM * p.ldp;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  EG_SET_SMEM_ONCE(attr_once,
+                   EG_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   dim3 grid((unsigned)pl.m_tiles, (unsigned)pl.n_tiles, (unsigned)pl.splits);
   gemm_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   EG_LAUNCHED();

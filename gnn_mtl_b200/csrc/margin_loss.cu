@@ -77,6 +77,9 @@ __device__ __forceinline__ void scatter_sign(const float* __restrict__ out, floa
   }
 }
 
+// WIDE: rows wider than the per-lane register accumulators (d > 512) — the anchor rows go through the
+// global atomics like every other row.
+template <bool WIDE>
 __global__ void __launch_bounds__(kMlWarps * 32)
 margin_loss_bwd_kernel(const float* __restrict__ out, int d, const int64_t* __restrict__ left,
                        const int64_t* __restrict__ right, const int64_t* __restrict__ nl,
@@ -87,6 +90,7 @@ margin_loss_bwd_kernel(const float* __restrict__ out, int d, const int64_t* __re
   const int64_t p = (int64_t)blockIdx.x * kMlWarps + warp;
   if (p >= t) return;
   const int64_t lp = left[p], rp = right[p];
+  const int64_t keep_l = WIDE ? -1 : lp, keep_r = WIDE ? -1 : rp;
   float acc_l[kMlMaxVec * 4], acc_r[kMlMaxVec * 4];       // this lane's columns of the two anchor rows (d <= 512)
 #pragma unroll
   for (int s = 0; s < kMlMaxVec * 4; ++s) { acc_l[s] = 0.f; acc_r[s] = 0.f; }
@@ -96,11 +100,12 @@ margin_loss_bwd_kernel(const float* __restrict__ out, int d, const int64_t* __re
   for (int q = 0; q < k; ++q) {
     const int64_t e = p * k + q;
     const float B1 = l1_rows(out + nl[e] * d, out + nr[e] * d, d, lane);
-    if (D - B1 > 0.f) { ++active; scatter_sign(out, grad, d, lane, nl[e], nr[e], -scale, lp, acc_l, rp, acc_r); }
+    if (D - B1 > 0.f) { ++active; scatter_sign(out, grad, d, lane, nl[e], nr[e], -scale, keep_l, acc_l, keep_r, acc_r); }
     const float B2 = l1_rows(out + n2l[e] * d, out + n2r[e] * d, d, lane);
-    if (D - B2 > 0.f) { ++active; scatter_sign(out, grad, d, lane, n2l[e], n2r[e], -scale, lp, acc_l, rp, acc_r); }
+    if (D - B2 > 0.f) { ++active; scatter_sign(out, grad, d, lane, n2l[e], n2r[e], -scale, keep_l, acc_l, keep_r, acc_r); }
   }
-  if (active) scatter_sign(out, grad, d, lane, lp, rp, scale * (float)active, lp, acc_l, rp, acc_r);
+  if (active) scatter_sign(out, grad, d, lane, lp, rp, scale * (float)active, keep_l, acc_l, keep_r, acc_r);
+  if (WIDE) return;
   int slot = 0;
   for (int kk = lane; kk < d; kk += 32, ++slot) {
     if (acc_l[slot] != 0.f) atomicAdd(grad + lp * d + kk, acc_l[slot]);
@@ -134,11 +139,14 @@ int eg_margin_loss_bwd(const float* out, int64_t n, int d, const int64_t* left, 
                        float gamma, float scale, float* grad, eg_stream_t stream_) {
   using namespace eg;
   if (t < 0 || k <= 0 || d <= 0 || n < 0) return EG_ERR_INVALID;
-  if (d > 32 * kMlMaxVec * 4) return EG_ERR_UNSUPPORTED;
   if (t == 0) return EG_OK;
   if (!out || !grad || !left || !right || !nl || !nr || !n2l || !n2r) return EG_ERR_INVALID;
-  margin_loss_bwd_kernel<<<(unsigned)ceil_div(t, kMlWarps), kMlWarps * 32, 0, as_stream(stream_)>>>(
-      out, d, left, right, nl, nr, n2l, n2r, t, k, gamma, scale, grad);
+  if (d > 32 * kMlMaxVec * 4)
+    margin_loss_bwd_kernel<true><<<(unsigned)ceil_div(t, kMlWarps), kMlWarps * 32, 0, as_stream(stream_)>>>(
+        out, d, left, right, nl, nr, n2l, n2r, t, k, gamma, scale, grad);
+  else
+    margin_loss_bwd_kernel<false><<<(unsigned)ceil_div(t, kMlWarps), kMlWarps * 32, 0, as_stream(stream_)>>>(
+        out, d, left, right, nl, nr, n2l, n2r, t, k, gamma, scale, grad);
   EG_LAUNCHED();
   return EG_OK;
 }

@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "sinkhorn_common.cuh"
 
 namespace eg {
 
@@ -309,24 +310,6 @@ static int plan_t(const T* M, int64_t n_rows, int64_t n_cols, int64_t ld, double
 // global synchronisation is two barriers per sweep.  Same init, order and stopping rule as
 // utils/ot_loss.py:38-70.
 
-struct PersistState {
-  unsigned int barrier;      // monotonically increasing arrival counter
-  int sweeps;                // sweeps completed (host output)
-  int final_buf;             // which log-v buffer holds the accepted iterate
-  double err;                // last marginal error evaluated
-  double err2[128];          // one accumulator per check (sweeps 0,10,...)
-  unsigned long long t_phase[8];   // ns spent by CTA 0 in C, barrier, R, barrier, U (diagnostic)
-  int fallback;              // scaling-domain kernel: a sum left the fp32 range -> caller redoes the solve in the log domain
-  int absorb_req;            // scaling-domain kernel: sweep (+1) at which every CTA folds u, v into its kernel entries
-  int absorbs;               // how many times that happened (diagnostic)
-};
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblocks) {
   __syncthreads();   // all of this CTA's writes are ordered before thread 0's release below (CTA-scope barrier)
   if (threadIdx.x == 0) {
@@ -566,19 +549,6 @@ constexpr int kOcQ = 2;     // column groups (float4) per thread
 constexpr int kOcRR = 5;    // rows kept in registers (phase C is written for exactly 4 + 1)
 static_assert(kOcRR == 5, "phase C unrolls the register rows as 4 + 1");
 
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2f(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
 // (max, sum) pair in log2 units; merge = one ex2 per operand.
 struct Lse2 {
   float m, s;
@@ -603,15 +573,23 @@ __device__ __forceinline__ void warp_merge2(Lse2& a) {
   a.s = sum;
 }
 
+__device__ int g_dev_sinkhorn_redos = 0;
+
 __global__ void __launch_bounds__(kOcThreads, 1)
 sinkhorn_onchip_kernel(const float* __restrict__ M, int64_t I, int J, int64_t ld, float inv_reg,
                        const float* __restrict__ log_a, const float* __restrict__ log_b, const float* __restrict__ b,
                        int max_iter, double stop_thr, float* __restrict__ part_m, float* __restrict__ part_s,
                        float* __restrict__ lv_buf, float* __restrict__ log_u_out, float* __restrict__ log_v_out,
-                       PersistState* __restrict__ st, int S_max) {
+                       PersistState* __restrict__ st, int S_max, const int* __restrict__ run_if) {
   using T = float;
   extern __shared__ __align__(16) unsigned char smem_raw_o[];
   const int nb = gridDim.x, cta = blockIdx.x;
+  // conditional launch (the redo after a scaling-domain solve that left the fp32 range): the flag was written by
+  // an earlier kernel on the same stream, every CTA reads the same value
+  if (run_if != nullptr) {
+    if (*run_if == 0) return;
+    if (cta == 0 && threadIdx.x == 0) atomicAdd(&g_dev_sinkhorn_redos, 1);
+  }
   const int rows_per = (int)((I + nb - 1) / nb);
   const int64_t row0 = min(I, (int64_t)cta * rows_per);
   const int R = (int)(min(I, row0 + rows_per) - row0);
@@ -1234,6 +1212,8 @@ struct SolveWs {
   double* err2;
   T *part_m, *part_s, *lv_buf;     // persistent-kernel scratch: [SMs, J] x2, [2, J]
   PersistState* state;
+  PersistState* state2;            // tile kernel (scaling-domain continuation)
+  PersistState* state3;            // conditional log-domain redo
   size_t total;
 };
 template <typename T>
@@ -1251,6 +1231,8 @@ static SolveWs<T> carve_solve(void* ws, int64_t I, int64_t J) {
   w.part_s = (T*)take(sizeof(T) * (size_t)kNumSMs * (size_t)J);
   w.lv_buf = (T*)take(sizeof(T) * 2 * (size_t)J);
   w.state = (PersistState*)take(sizeof(PersistState));
+  w.state2 = (PersistState*)take(sizeof(PersistState));
+  w.state3 = (PersistState*)take(sizeof(PersistState));
   w.total = off;
   return w;
 }
@@ -1261,8 +1243,16 @@ int g_tune_onchip = 1;       // eg_debug_set(5, 0) disables the fully on-chip fp
 int g_tune_scaling = 1;      // eg_debug_set(7, 0) keeps the whole on-chip solve in the log domain
 int g_tune_absorb_milli = 32000;   // eg_debug_set(10, x): fold u, v into the kernel once |log2| exceeds x / 1000
 int g_tune_force_fallback = 0;     // eg_debug_set(11, 1): treat every scaling-domain solve as failed (tests the redo path)
+int g_tune_tile2d = 1;              // eg_debug_set(12, 0): row-block scaling kernel instead of the 2-D tiled one
 int g_sinkhorn_fallbacks = 0;
 int g_sinkhorn_absorbs = 0;
+
+int sinkhorn_redo_count() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_dev_sinkhorn_redos, sizeof(int));
+  return g_sinkhorn_fallbacks + v;
+}
+int sinkhorn_absorb_count() { return g_sinkhorn_absorbs + sinkhorn_tile2d_absorbs_read(); }
 constexpr int kWarmSweeps = 4;   // log-domain sweeps before the scaling-domain kernel takes over
 
 // One cooperative launch for the whole solve when the shape allows it.
@@ -1302,15 +1292,21 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
         int64_t ld = J;
         int Ji = (int)J;
         PersistState host_state;
-        auto run_log = [&](int iters) -> int {
+        // one cooperative launch of the log-domain kernel; `run_if` != null makes it conditional on a device flag
+        auto launch_log = [&](int iters, PersistState* state, const int* run_if) -> int {
           fill_kernel<T><<<(unsigned)ceil_div(J, TB), TB, 0, s>>>(w.lv_buf, J, (T)(-log2((double)J))); EG_LAUNCHED();
-          EG_CUDA(cudaMemsetAsync(w.state, 0, sizeof(PersistState), s));
+          EG_CUDA(cudaMemsetAsync(state, 0, sizeof(PersistState), s));
           void* args[] = {(void*)&M, (void*)&I, (void*)&Ji, (void*)&ld, (void*)&inv_reg, (void*)&w.log_a,
                           (void*)&w.log_b, (void*)&b, (void*)&iters, (void*)&stop_thr, (void*)&w.part_m,
-                          (void*)&w.part_s, (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&w.state,
-                          (void*)&S_max};
+                          (void*)&w.part_s, (void*)&w.lv_buf, (void*)&log_u, (void*)&log_v, (void*)&state,
+                          (void*)&S_max, (void*)&run_if};
           EG_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)sms), dim3(kOcThreads), args, smem, s));
           g_launches.fetch_add(1, std::memory_order_relaxed);
+          return EG_OK;
+        };
+        auto run_log = [&](int iters) -> int {
+          int rc = launch_log(iters, w.state, nullptr);
+          if (rc) return rc;
           EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
           EG_CUDA(cudaStreamSynchronize(s));
           return EG_OK;
@@ -1325,9 +1321,53 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
                   full.t_phase[5] / 1e3 / full.sweeps, full.t_phase[6] / 1e3 / full.sweeps,
                   full.t_phase[7] / 1e3 / full.sweeps);
         };
+        // ---- default: warm-up -> 2-D tiled scaling kernel -> conditional redo, with NO host synchronisation unless
+        // the caller's stop rule needs the sweep count / error back (stop_thr >= 0)
+        bool warm_done = false;
+        if (g_tune_scaling && g_tune_tile2d && max_iter >= kWarmSweeps + 8) {
+          int rc = launch_log(kWarmSweeps, w.state, nullptr);
+          if (rc) return rc;
+          EG_CUDA(cudaMemsetAsync(w.state2, 0, sizeof(PersistState), s));
+          bool launched = false;
+          rc = sinkhorn_tile2d_launch(M, I, J, ld, 1.0 / reg, a, b, log_u, log_v, w.state, kWarmSweeps, max_iter,
+                                      stop_thr, w.part_m, (size_t)kNumSMs * (size_t)J, w.state2,
+                                      (float)g_tune_absorb_milli / 1000.0f, g_tune_force_fallback, s, &launched);
+          if (rc) return rc;
+          if (launched) {
+            rc = launch_log(max_iter, w.state3, &w.state2->fallback);
+            if (rc) return rc;
+            const bool timing = getenv("EG_PERSIST_TIMING") != nullptr;
+            if (stop_thr >= 0.0 || timing) {
+              PersistState hs[3];
+              EG_CUDA(cudaMemcpyAsync(&hs[0], w.state, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+              EG_CUDA(cudaMemcpyAsync(&hs[1], w.state2, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+              EG_CUDA(cudaMemcpyAsync(&hs[2], w.state3, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+              EG_CUDA(cudaStreamSynchronize(s));
+              const PersistState& fin = hs[0].sweeps < kWarmSweeps ? hs[0] : (hs[1].fallback ? hs[2] : hs[1]);
+              if (h_sweeps) *h_sweeps = fin.sweeps;
+              if (h_err) *h_err = fin.err;
+              if (timing && hs[1].sweeps > kWarmSweeps) {
+                const double n = hs[1].sweeps - kWarmSweeps;
+                fprintf(stderr, "[eagraft] tile2d sinkhorn: %d sweeps, fallback %d; CTA0 us/sweep: C %.2f | barrier %.2f | v %.2f | U dots %.2f | exchange+u %.2f\n",
+                        hs[1].sweeps, hs[1].fallback, hs[1].t_phase[0] / 1e3 / n, hs[1].t_phase[1] / 1e3 / n,
+                        hs[1].t_phase[2] / 1e3 / n, hs[1].t_phase[3] / 1e3 / n, hs[1].t_phase[4] / 1e3 / n);
+              }
+            } else {
+              // every sweep runs and nothing is read back: the whole solve stays asynchronous
+              if (h_sweeps) *h_sweeps = max_iter;
+              if (h_err) *h_err = -1.0;
+            }
+            *used = true;
+            return EG_OK;
+          }
+          // tile kernel not available for this shape / device: the warm-up result is reused below
+          EG_CUDA(cudaMemcpyAsync(&host_state, w.state, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+          EG_CUDA(cudaStreamSynchronize(s));
+          warm_done = true;
+        }
         bool done = false;
         if (g_tune_scaling && max_iter >= kWarmSweeps + 8 && ceil_div(J, (int64_t)sms) <= 32) {
-          int rc = run_log(kWarmSweeps);
+          int rc = warm_done ? EG_OK : run_log(kWarmSweeps);
           if (rc) return rc;
           report("log-domain warm-up");
           if (host_state.sweeps < kWarmSweeps) {
@@ -1434,6 +1474,7 @@ static int sinkhorn_dense_t(const T* M, int64_t I, int64_t J, double reg, const 
     if (prc) return prc;
     if (used) return EG_OK;
   }
+  if (Mt == nullptr) return EG_ERR_WORKSPACE;      // only this streaming path needs the transposed copy
   const double inv_reg = 1.0 / reg;
   const int TB = 256;
   int rc = transpose_t<T>(M, I, J, J, Mt, I, s);
@@ -1533,7 +1574,7 @@ int eg_sinkhorn_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, 
   using namespace eg;
   if (n_rows <= 0 || n_cols <= 0 || !(reg > 0.0) || max_iter < 0 || (dtype != 0 && dtype != 1))
     return EG_ERR_INVALID;
-  if (!M || !a || !b || !Mt || !log_u || !log_v || !ws) return EG_ERR_INVALID;
+  if (!M || !a || !b || !log_u || !log_v || !ws) return EG_ERR_INVALID;
   cudaStream_t s = as_stream(stream_);
   if (dtype == 0)
     return sinkhorn_dense_t<float>((const float*)M, n_rows, n_cols, reg, (const float*)a, (const float*)b,

@@ -479,13 +479,11 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
   p.normA = normA; p.normB = normB; p.pot_in = pot_in;
   p.A_raw = A_raw; p.B_raw = B_raw; p.d = d;
   pick_grid(nA, nB, &L->splits, &p.tiles_per_split);
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  EG_SET_SMEM_ONCE(attr_once,
+                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   return EG_OK;
 }
 }  // namespace tc
@@ -561,11 +559,9 @@ int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_
   p.pot_in = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
   p.bn = bn;
   p.tiles_per_split = (int)ceil_div(n, (int64_t)bn);
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once2;
+  EG_SET_SMEM_ONCE(attr_once2,
+                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(m, BM), kNumSMs), 1);    // persistent over row tiles
   lse_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
   EG_LAUNCHED();

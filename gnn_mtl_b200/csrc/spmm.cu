@@ -21,14 +21,6 @@ constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
 int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each)
 int g_tune_warps = 4;       // warps (= rows) per CTA
 int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelined SpMM with n CTAs per SM
-extern int g_tune_persistent;
-extern int g_tune_resident;
-extern int g_tune_onchip;
-extern int g_tune_scaling;
-extern int g_sinkhorn_fallbacks;
-extern int g_sinkhorn_absorbs;
-extern int g_tune_absorb_milli;
-extern int g_tune_force_fallback;
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
 
 struct Epilogue {
@@ -423,24 +415,6 @@ static int launch_vec(const int32_t* rowptr, const int32_t* col, const float* va
 }  // namespace eg
 
 extern "C" {
-
-// Undeclared tuning hook used by tools/ only (not part of include/eagraft.h).
-int eg_debug_set(int key, int value) {
-  if (key == 0) eg::g_tune_unroll = value;
-  else if (key == 1) eg::g_tune_warps = value;
-  else if (key == 2) eg::g_tune_hints = value;
-  else if (key == 3) eg::g_tune_persistent = value;
-  else if (key == 4) eg::g_tune_resident = value;
-  else if (key == 5) eg::g_tune_onchip = value;
-  else if (key == 6) eg::g_tune_spmm_persist = value;
-  else if (key == 7) eg::g_tune_scaling = value;                  // 0: log-domain on-chip Sinkhorn only
-  else if (key == 8) return eg::g_sinkhorn_fallbacks;             // query: scaling-domain solves redone in the log domain
-  else if (key == 9) return eg::g_sinkhorn_absorbs;               // query: absorptions in the last scaling-domain solve
-  else if (key == 10) eg::g_tune_absorb_milli = value;
-  else if (key == 11) eg::g_tune_force_fallback = value;
-  else return EG_ERR_INVALID;
-  return EG_OK;
-}
 
 int eg_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows, const float* H,
             int d, int act, const float* gate_pre, const float* x_res, float* out, float* act_out,

@@ -5,9 +5,9 @@ the reference's layers/layers.py (GraphConvolution :19-42, HighWayGraphConvoluti
 :45-80, Linear :83-96, get_dim_act :8-16), so models/encoders.py-style glue works
 unchanged.  What differs is the execution: the sparse aggregation, activation and
 highway blend run as ONE CUDA kernel (eg_spmm), and the backward is a fused
-element-wise kernel followed by the same SpMM on the transposed CSR.  The two
-small dense GEMMs per layer (x·Wᵀ + b and x·G + c) stay on cuBLAS through PyTorch
-(SURVEY.md §2.1 K1/K5).
+element-wise kernel followed by the same SpMM on the transposed CSR.  The dense
+products of a layer (x·Wᵀ + b, x·G + c, dx, dW/db) run on the tcgen05 3xTF32
+GEMM kernels (eg_gemm_nt_3xtf32 / eg_gemm_tn_3xtf32); see ``_DenseProducts``.
 """
 from __future__ import annotations
 
@@ -35,10 +35,14 @@ def classify_activation(act):
         return _lib.ACT_IDENTITY
     if act in (F.relu, torch.relu):
         return _lib.ACT_RELU
-    probe = torch.tensor([-2.0, -0.5, 0.0, 0.75, 3.0])
+    # Anything else is probed on a wide range (so clamped variants such as relu6 / hardtanh differ from relu)
+    # with a fresh clone per call (an in-place activation must not alias the comparison value).
+    probe = torch.tensor([-1e4, -100.0, -7.0, -2.0, -0.5, -1e-3, 0.0, 1e-3, 0.75, 3.0, 6.5, 100.0, 1e4])
     try:
-        got = act(probe)
+        got = act(probe.clone())
     except Exception:
+        return None
+    if not torch.is_tensor(got) or got.shape != probe.shape:
         return None
     if torch.equal(got, probe):
         return _lib.ACT_IDENTITY
@@ -181,8 +185,9 @@ class _DenseProducts(torch.autograd.Function):
 
 
 def _tc_gemm_ok(x, linear, gate_w=None):
+    # in_features % 4: the backward dx product writes rows of in_features floats through the same kernel
     return (USE_TCGEN05_GEMM and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
-            and linear.out_features % 4 == 0 and x.shape[0] > 0
+            and linear.out_features % 4 == 0 and x.shape[1] % 4 == 0 and x.shape[0] > 0
             and (gate_w is None or gate_w.shape[1] % 4 == 0))
 
 

@@ -268,7 +268,6 @@ def sinkhorn_dense(M, a, b, reg, max_iter, stop_thr):
     dt = _dt(M)
     I, J = M.shape
     dev = M.device
-    Mt = torch.empty(J, I, dtype=M.dtype, device=dev)
     log_u = torch.empty(I, dtype=M.dtype, device=dev)
     log_v = torch.empty(J, dtype=M.dtype, device=dev)
     with torch.cuda.device(dev):
@@ -278,9 +277,15 @@ def sinkhorn_dense(M, a, b, reg, max_iter, stop_thr):
         if SINKHORN_TIMER is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        check(lib.eg_sinkhorn_dense(dt, ptr(M), I, J, float(reg), ptr(a), ptr(b), int(max_iter), float(stop_thr),
-                                    ptr(Mt), ptr(log_u), ptr(log_v), ptr(ws), ws_bytes, C.byref(sweeps),
-                                    C.byref(err), stream()), "eg_sinkhorn_dense")
+        rc = lib.eg_sinkhorn_dense(dt, ptr(M), I, J, float(reg), ptr(a), ptr(b), int(max_iter), float(stop_thr),
+                                   None, ptr(log_u), ptr(log_v), ptr(ws), ws_bytes, C.byref(sweeps),
+                                   C.byref(err), stream())
+        if rc == -3:    # EG_ERR_WORKSPACE: this shape takes the streaming path, which wants the transposed copy
+            Mt = torch.empty(J, I, dtype=M.dtype, device=dev)
+            rc = lib.eg_sinkhorn_dense(dt, ptr(M), I, J, float(reg), ptr(a), ptr(b), int(max_iter), float(stop_thr),
+                                       ptr(Mt), ptr(log_u), ptr(log_v), ptr(ws), ws_bytes, C.byref(sweeps),
+                                       C.byref(err), stream())
+        check(rc, "eg_sinkhorn_dense")
         if SINKHORN_TIMER is not None:
             ev1.record()
             SINKHORN_TIMER.append((ev0, ev1, I, J, int(sweeps.value), M.element_size()))
@@ -441,15 +446,44 @@ class _MarginLoss(torch.autograd.Function):
         return grad, None, None, None, None, None, None, None, None
 
 
+_MARGIN_INDEX_OK = {}     # what -> (data_ptr, numel, version, n) of device index tensors already range-checked
+
+
+def _row_indices(idx, n, what, dev):
+    """int64 CUDA copy of an index array, range-checked against [0, n): the kernels index ``outputs`` without
+    bounds checks where the reference's fancy indexing raises IndexError (models/models_ea.py:108-118).  Host
+    arrays (what the reference's models hold) are checked on the host before the upload; device tensors with one
+    device-side min/max per *new* tensor, so the steady-state step adds no host synchronisation."""
+    import numpy as np
+    if not torch.is_tensor(idx) or not idx.is_cuda:
+        host = idx.numpy() if torch.is_tensor(idx) else np.asarray(idx)
+        if host.size and (host.min() < 0 or host.max() >= n):
+            raise IndexError("margin_loss: %s has an index outside [0, %d) (min %d, max %d)"
+                             % (what, n, int(host.min()), int(host.max())))
+        return torch.as_tensor(host).to(device=dev, dtype=torch.int64).contiguous()
+    idx = idx.to(device=dev, dtype=torch.int64).contiguous()
+    key = (idx.data_ptr(), idx.numel(), idx._version, int(n))
+    if idx.numel() and _MARGIN_INDEX_OK.get(what) != key:
+        lo, hi = (int(v) for v in torch.aminmax(idx))
+        if lo < 0 or hi >= n:
+            raise IndexError("margin_loss: %s has an index outside [0, %d) (min %d, max %d)" % (what, n, lo, hi))
+        _MARGIN_INDEX_OK[what] = key
+    return idx
+
+
 def margin_loss(outputs, left, right, nl, nr, n2l, n2r, k, gamma=1.0):
     """(sum relu(A+gamma-B1) + sum relu(A+gamma-B2)) / (2 t k) — models/models_ea.py:103-123."""
     _lib.require_cuda(outputs)
     dev = outputs.device
 
-    def ix(a):
-        a = a if torch.is_tensor(a) else torch.as_tensor(a)
-        return a.to(device=dev, dtype=torch.int64).contiguous()
-    return _MarginLoss.apply(outputs, ix(left), ix(right), ix(nl), ix(nr), ix(n2l), ix(n2r), k, gamma)
+    def ix(a, what):
+        return _row_indices(a, outputs.shape[0], what, dev)
+    left, right = ix(left, "left"), ix(right, "right")
+    nl, nr, n2l, n2r = ix(nl, "neg_left"), ix(nr, "neg_right"), ix(n2l, "neg2_left"), ix(n2r, "neg2_right")
+    if not (left.numel() == right.numel() and nl.numel() == nr.numel() == n2l.numel() == n2r.numel()
+            == left.numel() * int(k)):
+        raise ValueError("margin_loss: index arrays disagree (t = %d, k = %d)" % (left.numel(), int(k)))
+    return _MarginLoss.apply(outputs, left, right, nl, nr, n2l, n2r, k, gamma)
 
 
 # ---- GAT edge-softmax aggregation (layers/att_layers.py:29-61) ------------------------------------

@@ -54,7 +54,7 @@ def train_ea(args, data=None, log=print):
                 best_val, best_test, counter = val_metrics, val_metrics, 0
             else:
                 counter += 1
-                if counter == args.patience and epoch > args.min_epochs:
+                if counter >= args.patience and epoch > args.min_epochs:
                     log("Early stopping")
                     break
     log('Total time elapsed: {:.4f}s'.format(time.time() - t_total))

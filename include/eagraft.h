@@ -51,6 +51,18 @@ int eg_device_check(void);             /* EG_OK iff current device is compute ca
 int64_t eg_launch_count(void);         /* kernels launched by this library since reset */
 void eg_launch_count_reset(void);
 
+/* Diagnostics / kernel-variant selection for tests and tools.  NOT part of the data path: production callers
+ * never call it and every knob defaults to the shipping kernel.  The knobs are process-global plain ints, so —
+ * unlike every other entry point, which may be called concurrently from several host threads on different
+ * streams — this call must not race with calls that are inside the library.
+ *   set (returns EG_OK):  0/1 SpMM rows-in-flight / warps per CTA, 2 SpMM L2 hints, 3 persistent Sinkhorn on/off,
+ *     4 resident rows on/off, 5 on-chip fp32 Sinkhorn on/off, 6 persistent SpMM CTAs per SM, 7 scaling-domain
+ *     continuation on/off, 10 fold threshold (|log2| x 1000), 11 force the log-domain redo, 12 2-D tiled scaling
+ *     kernel on/off (off: row-block kernel), 13 fp32 candidate filter of the L1 rank kernels on/off
+ *   query (value ignored): 8 scaling-domain solves redone in the log domain so far, 9 fold steps so far
+ * Queries 8/9 read device counters and synchronise the device. */
+int eg_debug_set(int key, int value);
+
 /* ---- (A) adjacency: triples -> degree-normalised CSR -------------------------
  * Replaces utils/data_utils.py:296-336 (get_matrix, get_sparse_tensor) and the
  * fp64->fp32 cast of sparse_mx_to_torch_sparse_tensor (:51-57).  Output equals
@@ -163,9 +175,13 @@ int eg_plan_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, int6
                   void* row_sum, void* col_sum, eg_stream_t stream);
 /* Whole solver of utils/ot_loss.py:26-76 on the device (materialised cost):
  * u0 = 1/I, v0 = 1/J, column then row update per sweep, marginal-error check on
- * sweeps 0,10,20,…, stop at err <= stop_thr or max_iter.  Mt is scratch for the
- * transposed cost [n_cols, n_rows].  log_u/log_v receive the final log-scalings.
- * SYNCHRONOUS every 10 sweeps (error read-back), h_* are host outputs. */
+ * sweeps 0,10,20,…, stop at err <= stop_thr or max_iter.  log_u/log_v receive the final log-scalings.
+ * Mt is scratch for the transposed cost [n_cols, n_rows]; only the streaming path (shapes the one-launch
+ * kernels cannot take) needs it: pass NULL to skip the allocation — the call then returns
+ * EG_ERR_WORKSPACE, before doing any work, when that path is required.
+ * h_sweeps / h_err are host outputs.  Synchronisation: with stop_thr >= 0 the call waits for the solve (the
+ * sweep count and error are results); with stop_thr < 0 ("run every sweep") on the one-launch fp32 path
+ * nothing is read back — the call is ASYNCHRONOUS, *h_sweeps = max_iter and *h_err = -1. */
 int eg_sinkhorn_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, double reg,
                       const void* a, const void* b, int max_iter, double stop_thr,
                       void* Mt, void* log_u, void* log_v, void* ws, size_t ws_bytes,

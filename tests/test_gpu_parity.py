@@ -121,9 +121,10 @@ def _oracle_stack(kg, x, params, acts):
     return xs, ps, y
 
 
-@pytest.mark.parametrize("shape,dim", [("tiny", 300), ("tiny", 128), ("tiny", 50), ("dbp15k", 300)])
+@pytest.mark.parametrize("shape,dim", [("tiny", 300), ("tiny", 128), ("tiny", 50), ("dbp15k", 300), ("dbp100k", 300)])
 def test_hgcn_stack_vs_oracle(shape, dim, dev):
-    """2 encoder + 1 decoder highway layers (models/encoders.py:53-66, decoders.py:40-47)."""
+    """2 encoder + 1 decoder highway layers (models/encoders.py:53-66, decoders.py:40-47); the last case is the
+    benchmark's own graph (200k nodes, BASELINE.json config 3): forward and every gradient against the oracle."""
     from gnn_mtl_b200.adjacency import DeviceAdjacency
     from gnn_mtl_b200.layers.layers import HighWayGraphConvolution
     from gnn_mtl_b200.synth import make_kg_pair

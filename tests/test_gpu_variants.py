@@ -63,12 +63,13 @@ def test_sinkhorn_scaling_domain_continuation(I, J, reg, iters, dev):
     M = M * 1.5
     _, loss_ref, ref = orc.sinkhorn_scaling(a, b, M, reg, numItermax=iters, stopThr=-1.0, return_info=True)
     dbg = _lib.lib.eg_debug_set
-    out = {}
+    out, raw = {}, {}
     try:
-        for name, knobs in (("scaling", {}), ("log", {7: 0}), ("absorb_often", {10: 10}), ("forced_redo", {11: 1})):
+        for name, knobs in (("scaling", {}), ("rowblock", {12: 0}), ("log", {7: 0}), ("absorb_often", {10: 10}),
+                            ("absorb_often_rowblock", {10: 10, 12: 0}), ("forced_redo", {11: 1})):
             for key, val in knobs.items():
                 dbg(key, val)
-            fallbacks0 = dbg(8, 0)
+            fallbacks0, folds0 = dbg(8, 0), dbg(9, 0)
             info = {}
             _, loss = sinkhorn(a.to(dev), b.to(dev), M.to(dev), reg, numItermax=iters, stopThr=-1.0, return_plan=False,
                                info=info)
@@ -76,21 +77,25 @@ def test_sinkhorn_scaling_domain_continuation(I, J, reg, iters, dev):
             # potentials are fixed up to the (c, -c) shift the iteration itself leaves free: compare u_i + v_j
             got = info["log_u"].double().cpu()[:, None] + info["log_v"].double().cpu()[None, :64]
             want = ref["log_u"].double()[:, None] + ref["log_v"].double()[None, :64]
-            assert float((got - want).abs().max()) < 2e-4 * max(1.0, float(want.abs().max())), name
+            assert float((got - want).abs().max()) < 1e-4, name       # absolute, log units
             assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < 1e-4, name
-            if name == "absorb_often":
-                assert dbg(9, 0) > 0                      # the fold step really ran
+            if name.startswith("absorb_often"):
+                assert dbg(9, 0) > folds0                 # the fold step really ran
             if name == "forced_redo":
                 assert dbg(8, 0) == fallbacks0 + 1
             if name == "scaling":
                 assert dbg(8, 0) == fallbacks0           # and did not need the redo
-            out[name] = info["log_u"].double().cpu()
+            out[name] = got
+            raw[name] = info["log_u"].double().cpu()
             for key in knobs:
-                dbg(key, {7: 1, 10: 32000, 11: 0}[key])
+                dbg(key, {7: 1, 10: 32000, 11: 0, 12: 1}[key])
     finally:
-        dbg(7, 1); dbg(10, 32000); dbg(11, 0)
-    assert float((out["forced_redo"] - out["log"]).abs().max()) == 0.0     # the redo IS the log-domain kernel
-    assert relerr(out["scaling"], out["log"]) < 1e-4 and relerr(out["absorb_often"], out["log"]) < 1e-4
+        dbg(7, 1); dbg(10, 32000); dbg(11, 0); dbg(12, 1)
+    assert float((raw["forced_redo"] - raw["log"]).abs().max()) == 0.0     # the redo IS the log-domain kernel
+    # absolute, log units (the log-domain kernel carries potentials of O(100) in fp32: ~3e-5 of rounding itself)
+    assert float((out["scaling"] - out["log"]).abs().max()) < 1e-4
+    assert float((out["rowblock"] - out["log"]).abs().max()) < 1e-4
+    assert float((out["absorb_often"] - out["log"]).abs().max()) < 1e-4
 
 
 def test_sinkhorn_fp64_persistent_vs_streaming(dev):
