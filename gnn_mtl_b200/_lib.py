@@ -47,6 +47,7 @@ SIGNATURES = {
     "eg_transpose": (C.c_int, [_i32, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "eg_plan_dense": (C.c_int, [_i32, _vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "eg_sinkhorn_dense_workspace_bytes": (_sz, [_i32, _i64, _i64]),
+    "eg_sinkhorn_sync_floor": (C.c_int, [_i64, _i64, _i32, _vp, _sz, _vp]),
     "eg_sinkhorn_dense": (C.c_int, [_i32, _vp, _i64, _i64, _f64, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _sz,
                                     C.POINTER(C.c_int), C.POINTER(_f64), _vp]),
     "eg_row_norms": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
@@ -58,11 +59,15 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp]),
     "eg_gemm_nt_3xtf32": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp,
                                     _i64, _vp]),
+    "eg_gemm_nt_3xtf32_signsafe": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64,
+                                             _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "eg_margin_loss_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp]),
     "eg_margin_loss_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),
     "eg_gemm_tn_3xtf32_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "eg_gemm_tn_3xtf32": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i64, _vp, _sz, _vp, _i64, _vp]),
     "eg_l1_rank_fused": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "eg_l1_rank_filtered_workspace_bytes": (_sz, [_i64, _i64]),
+    "eg_l1_rank_filtered": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eg_l1_topk_fused_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "eg_l1_topk_fused": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "eg_gat_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp,

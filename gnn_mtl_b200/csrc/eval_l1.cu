@@ -175,7 +175,8 @@ l1_tile_kernel(const float* __restrict__ L, int64_t nL, const float* __restrict_
 __global__ void __launch_bounds__(128, 3)
 l1_rank_fused_kernel(const float* __restrict__ L, int64_t nL, int64_t row0, const float* __restrict__ R, int64_t nR,
                      int d, int tiles_per_cta, const double* __restrict__ diag, int32_t* __restrict__ rank_row,
-                     int32_t* __restrict__ rank_col) {
+                     int32_t* __restrict__ rank_col, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;       // conditional launch (fallback of the filtered path)
   __shared__ __align__(16) double Ls[kKC8][kPad];
   __shared__ __align__(16) double Rs[kKC8][kPad];
   __shared__ int col_cnt_s[2][kTile];
@@ -630,6 +631,23 @@ static int topk_segments(int64_t nL, int64_t nR, int* tiles_per_cta) {
   return (int)ceil_div(col_tiles, per);
 }
 
+// rank_row[row0 .. row0 + nL) must be zero on entry when run_if is given (the filtered path leaves it untouched
+// on overflow and the caller zeroes it up front); the unconditional call zeroes it itself.
+int l1_rank_exact_launch(const float* L, int64_t nL, int64_t row0, const float* R, int64_t nR, int d,
+                         const double* diag, int32_t* rank_row, int32_t* rank_col, const int* run_if, cudaStream_t s) {
+  const int64_t gy = ceil_div(nL, kTile), col_tiles = ceil_div(nR, kTile);
+  if (gy > 65535) return EG_ERR_UNSUPPORTED;
+  // column segments per strip: enough CTAs for ~8 per SM overall, at most one per column tile
+  int64_t n_seg = std::max<int64_t>(1, std::min<int64_t>(col_tiles, ceil_div((int64_t)(8 * 148), gy)));
+  const int per = (int)ceil_div(col_tiles, n_seg);
+  n_seg = ceil_div(col_tiles, (int64_t)per);
+  if (run_if == nullptr) EG_CUDA(cudaMemsetAsync(rank_row + row0, 0, sizeof(int32_t) * (size_t)nL, s));
+  dim3 grid((unsigned)n_seg, (unsigned)gy);
+  l1_rank_fused_kernel<<<grid, 128, 0, s>>>(L, nL, row0, R, nR, d, per, diag, rank_row, rank_col, run_if);
+  EG_LAUNCHED();
+  return EG_OK;
+}
+
 }  // namespace eg
 
 extern "C" {
@@ -640,18 +658,7 @@ int eg_l1_rank_fused(const float* L, int64_t nL, int64_t row0, const float* R, i
   if (nL < 0 || nR < 0 || row0 < 0 || d <= 0 || row0 + nL > nR) return EG_ERR_INVALID;
   if (nL == 0 || nR == 0) return EG_OK;
   if (!L || !R || !diag || !rank_row || !rank_col) return EG_ERR_INVALID;
-  const int64_t gy = ceil_div(nL, kTile), col_tiles = ceil_div(nR, kTile);
-  if (gy > 65535) return EG_ERR_UNSUPPORTED;
-  // column segments per strip: enough CTAs for ~8 per SM overall, at most one per column tile
-  int64_t n_seg = std::max<int64_t>(1, std::min<int64_t>(col_tiles, ceil_div((int64_t)(8 * 148), gy)));
-  const int per = (int)ceil_div(col_tiles, n_seg);
-  n_seg = ceil_div(col_tiles, (int64_t)per);
-  cudaStream_t s = as_stream(stream_);
-  EG_CUDA(cudaMemsetAsync(rank_row + row0, 0, sizeof(int32_t) * (size_t)nL, s));
-  dim3 grid((unsigned)n_seg, (unsigned)gy);
-  l1_rank_fused_kernel<<<grid, 128, 0, s>>>(L, nL, row0, R, nR, d, per, diag, rank_row, rank_col);
-  EG_LAUNCHED();
-  return EG_OK;
+  return l1_rank_exact_launch(L, nL, row0, R, nR, d, diag, rank_row, rank_col, nullptr, as_stream(stream_));
 }
 
 size_t eg_l1_topk_fused_workspace_bytes(int64_t nL, int64_t nR, int skip, int k) {

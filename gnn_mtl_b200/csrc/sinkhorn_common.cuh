@@ -48,4 +48,8 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
                            int max_iter, double stop_thr, float* part, size_t part_floats, PersistState* st,
                            float absorb_log2, int force_fallback, cudaStream_t s, bool* launched);
 
+// Communication skeleton of one tile-kernel sweep (no mat-vec work), `iters` times: the latency floor of the design.
+int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* part, size_t part_floats,
+                                      PersistState* st, cudaStream_t s, bool* launched);
+
 }  // namespace eg

@@ -1562,6 +1562,18 @@ int eg_plan_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, int6
                         (double*)P, ldP, loss, (double*)row_sum, (double*)col_sum, s);
 }
 
+int eg_sinkhorn_sync_floor(int64_t n_rows, int64_t n_cols, int iters, void* ws, size_t ws_bytes, eg_stream_t stream_) {
+  using namespace eg;
+  if (n_rows <= 0 || n_cols <= 0 || iters <= 0 || !ws) return EG_ERR_INVALID;
+  SolveWs<float> w = carve_solve<float>(ws, n_rows, n_cols);
+  if (ws_bytes < w.total) return EG_ERR_WORKSPACE;
+  bool launched = false;
+  int rc = sinkhorn_tile2d_sync_floor_launch(n_rows, n_cols, iters, w.part_m, (size_t)kNumSMs * (size_t)n_cols, w.state2,
+                                             as_stream(stream_), &launched);
+  if (rc) return rc;
+  return launched ? EG_OK : EG_ERR_UNSUPPORTED;
+}
+
 size_t eg_sinkhorn_dense_workspace_bytes(int dtype, int64_t n_rows, int64_t n_cols) {
   if (n_rows <= 0 || n_cols <= 0) return 0;
   return dtype == 0 ? eg::carve_solve<float>(nullptr, n_rows, n_cols).total

@@ -486,10 +486,132 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   }
 }
 
+// The communication skeleton of one sweep with no mat-vec work: column partials through global memory + the grid
+// barrier + NC partial reads, then the row-partial push through distributed shared memory + the cluster barrier.
+// bench.py times it to state the latency floor of this design next to the measured sweep time.
+__global__ void __launch_bounds__(kT2Threads, 1)
+sinkhorn_tile2d_sync_floor_kernel(PersistState* st, float* part, int NC, int Gs, int nrw, int iters) {
+  extern __shared__ __align__(16) unsigned char smem_raw_t2[];
+  float* sm = reinterpret_cast<float*>(smem_raw_t2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = (int)cluster_ctarank(), p = (int)cluster_idx();
+  const unsigned int nb = (unsigned int)(NC * kT2CS);
+  const int nc4 = Gs * 4, rb_pad = kT2Warps * nrw + kT2MaxRowsPerWarp;
+  const T2Smem L = t2_carve(nrw, Gs);
+  float* u_s = sm + L.u; float* v_s = sm + L.v; float* red_c = sm + L.red_c; float* rowpart = sm + L.rowpart;
+  const uint32_t rowpart_saddr = (uint32_t)__cvta_generic_to_shared(rowpart);
+  for (int i = tid; i < kT2Warps * nc4; i += kT2Threads) red_c[i] = 1.0f;
+  for (int i = tid; i < rb_pad; i += kT2Threads) u_s[i] = 1.0f;
+  __syncthreads();
+  unsigned int target = 0;
+  for (int it = 0; it < iters; ++it) {
+    const int par = it & 1;
+    __syncthreads();
+    float* my_part = part + ((size_t)(par * kT2CS + q) * NC) * nc4;
+    if (tid < nc4) {
+      float s = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kT2Warps; ++w2) s += red_c[w2 * nc4 + tid];
+      my_part[(size_t)p * nc4 + tid] = s * u_s[0];
+    }
+    t2_grid_barrier(st, target, nb);
+    if (tid < nc4) {
+      float s = 0.f;
+      for (int pp = 0; pp < NC; ++pp) s += ld_relaxed_f32(my_part + (size_t)pp * nc4 + tid);
+      v_s[tid] = 1.0f / s;
+    }
+    __syncthreads();
+    const float tot = v_s[lane];
+    const int r = lane & 15;
+    if (r < nrw) {
+      const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * rb_pad + warp * nrw + r);
+      const int q0 = (lane >> 4) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st_cluster_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot);
+    }
+    cluster_sync_all();
+    if (tid < kT2Warps * nrw) {
+      const float* rp = rowpart + (par * kT2CS) * rb_pad + tid;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kT2CS; ++k) s += rp[k * rb_pad];
+      u_s[tid] = 1.0f / s;
+    }
+  }
+}
+
 int sinkhorn_tile2d_absorbs_read() {
   int v = 0;
   cudaMemcpyFromSymbol(&v, g_dev_tile2d_absorbs, sizeof(int));
   return v;
+}
+
+// Launch geometry: the fewest rows per warp for which the co-resident clusters cover all rows.
+struct T2Geometry { int nc, nrw, gs, rows_per_cluster; size_t smem; };
+template <typename Kern>
+static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, T2Geometry* g, cudaLaunchConfig_t* cfg,
+                       cudaLaunchAttribute* attrs) {
+  g->nc = 0;
+  int dev = 0, max_smem = 0;
+  EG_CUDA(cudaGetDevice(&dev));
+  EG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  g->gs = (int)ceil_div(J / 4, (int64_t)kT2CS);
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kT2CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  *cfg = cudaLaunchConfig_t{};
+  cfg->blockDim = dim3(kT2Threads);
+  cfg->stream = s;
+  cfg->attrs = attrs;
+  for (int try_nrw = 1; try_nrw <= kT2MaxRowsPerWarp; ++try_nrw) {
+    const T2Smem L = t2_carve(try_nrw, g->gs);
+    if (L.bytes > (size_t)max_smem) break;
+    EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+    cfg->gridDim = dim3(kT2CS * kT2MaxClusters);
+    cfg->dynamicSmemBytes = L.bytes;
+    cfg->numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg) != cudaSuccess) { cudaGetLastError(); return EG_OK; }
+    max_clusters = std::min(max_clusters, kT2MaxClusters);
+    if (max_clusters < 4) continue;
+    if ((int64_t)max_clusters * kT2Warps * try_nrw >= I) {
+      g->nrw = try_nrw;
+      g->nc = (int)std::min<int64_t>(max_clusters, ceil_div(I, (int64_t)kT2Warps * try_nrw));
+      g->smem = L.bytes;
+      break;
+    }
+  }
+  if (g->nc == 0) return EG_OK;
+  g->rows_per_cluster = (int)ceil_div(I, (int64_t)g->nc);
+  cfg->gridDim = dim3((unsigned)(kT2CS * g->nc));
+  cfg->dynamicSmemBytes = g->smem;
+  cfg->numAttrs = 2;
+  return EG_OK;
+}
+
+int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* part, size_t part_floats,
+                                      PersistState* st, cudaStream_t s, bool* launched) {
+  *launched = false;
+  if (J % 4 != 0 || J > 4 * kT2CS * 32 * kT2QG || iters <= 0) return EG_OK;
+  T2Geometry g;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attrs[2];
+  auto kern = sinkhorn_tile2d_sync_floor_kernel;
+  int rc = t2_geometry(kern, I, J, s, &g, &cfg, attrs);
+  if (rc) return rc;
+  if (g.nc == 0 || (size_t)2 * kT2CS * g.nc * g.gs * 4 > part_floats) return EG_OK;
+  EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, part, g.nc, g.gs, g.nrw, iters);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, st, part, g.nc, g.gs, g.nrw, iters);
+    if (e != cudaSuccess) { cudaGetLastError(); return EG_OK; }
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  *launched = true;
+  return EG_OK;
 }
 
 int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, double inv_reg, const float* a,
@@ -498,55 +620,19 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
                            float absorb_log2, int force_fallback, cudaStream_t s, bool* launched) {
   *launched = false;
   if (J % 4 != 0 || (reinterpret_cast<uintptr_t>(M) & 15) || (ld % 4) != 0 || J > 4 * kT2CS * 32 * kT2QG) return EG_OK;
-  int dev = 0, max_smem = 0;
-  EG_CUDA(cudaGetDevice(&dev));
-  EG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int gs = (int)ceil_div(J / 4, (int64_t)kT2CS);
-  auto kern = sinkhorn_tile2d_kernel;
-  // the tile must fit for the cluster count the device can keep resident: try the largest shared-memory request
-  // first (fewest clusters needed), query how many clusters are co-resident with it, then size the tile
-  cudaLaunchConfig_t cfg = {};
+  T2Geometry g;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = kT2CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeCooperative;
-  attrs[1].val.cooperative = 1;
-  cfg.blockDim = dim3(kT2Threads);
-  cfg.stream = s;
-  cfg.attrs = attrs;
-  int nc = 0, nrw = 0;
-  size_t smem = 0;
-  for (int try_nrw = 1; try_nrw <= kT2MaxRowsPerWarp; ++try_nrw) {
-    const T2Smem L = t2_carve(try_nrw, gs);
-    if (L.bytes > (size_t)max_smem) break;
-    EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-    cfg.gridDim = dim3(kT2CS * kT2MaxClusters);
-    cfg.dynamicSmemBytes = L.bytes;
-    cfg.numAttrs = 1;
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return EG_OK; }
-    max_clusters = std::min(max_clusters, kT2MaxClusters);
-    if (max_clusters < 4) continue;
-    if ((int64_t)max_clusters * kT2Warps * try_nrw >= I) {
-      // fewest rows per warp that covers I; spread the rows evenly over the clusters in use
-      nrw = try_nrw;
-      nc = (int)std::min<int64_t>(max_clusters, ceil_div(I, (int64_t)kT2Warps * nrw));
-      smem = L.bytes;
-      break;
-    }
-  }
-  if (nc == 0) return EG_OK;
-  const int rows_per_cluster = (int)ceil_div(I, (int64_t)nc);
-  if ((size_t)2 * kT2CS * nc * gs * 4 > part_floats) return EG_OK;
+  auto kern = sinkhorn_tile2d_kernel;
+  int rc = t2_geometry(kern, I, J, s, &g, &cfg, attrs);
+  if (rc) return rc;
+  if (g.nc == 0 || (size_t)2 * kT2CS * g.nc * g.gs * 4 > part_floats) return EG_OK;
   T2Params P;
-  P.M = M; P.I = I; P.J = (int)J; P.ld = ld; P.inv2 = inv_reg * 1.4426950408889634074; P.a = a; P.b = b; P.log_u = log_u; P.log_v = log_v;
+  P.M = M; P.I = I; P.J = (int)J; P.ld = ld; P.inv2 = inv_reg * 1.4426950408889634074;
+  P.a = a; P.b = b; P.log_u = log_u; P.log_v = log_v;
   P.warm = warm; P.start_iter = start_iter; P.max_iter = max_iter; P.stop_thr = stop_thr; P.part = part; P.st = st;
-  P.nc = nc; P.rows_per_cluster = rows_per_cluster; P.nrw = nrw; P.gs = gs; P.absorb_log2 = absorb_log2;
+  P.nc = g.nc; P.rows_per_cluster = g.rows_per_cluster; P.nrw = g.nrw; P.gs = g.gs; P.absorb_log2 = absorb_log2;
   P.force_fallback = force_fallback;
-  EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cfg.gridDim = dim3((unsigned)(kT2CS * nc));
-  cfg.dynamicSmemBytes = smem;
-  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
   if (e != cudaSuccess) {
     // cooperative + cluster refused by this driver: the occupancy query above already guarantees that the whole
@@ -559,7 +645,7 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (getenv("EG_PERSIST_TIMING"))
     fprintf(stderr, "[eagraft] tile2d sinkhorn: %d clusters x %d CTAs, %d rows/cluster, %d rows/warp, %d groups/slice, %zu B smem\n",
-            nc, kT2CS, rows_per_cluster, nrw, gs, smem);
+            g.nc, kT2CS, g.rows_per_cluster, g.nrw, g.gs, g.smem);
   *launched = true;
   return EG_OK;
 }

@@ -113,29 +113,48 @@ def topk_rows(D, skip, k):
 FUSED_ROW_CHUNK = 65535 * 64      # rows per streamed launch (grid.y limit x 64-row strips)
 
 
-def l1_rank_fused(L_block, row0, R, diag, rank_row, rank_col):
+L1_RANK_FILTER = True              # fp32 candidate filter + exact fp64 decisions (identical ranks); False: all fp64
+FILTER_PAIRS_PER_CALL = 1 << 35   # bounds the candidate queue (pairs / 256 entries of 8 bytes) to ~1 GiB
+
+
+def l1_rank_fused(L_block, row0, R, diag, rank_row, rank_col, filtered=None):
     """Streamed rank counts for rows [row0, row0 + len(L_block)) of the L1 matrix against all of R: nothing of
     size rows x cols is stored.  rank_row[row0:...] is overwritten, rank_col accumulated."""
     _lib.require_cuda(L_block, R, diag, rank_row, rank_col)
     L_block, R = _f32c(L_block), _f32c(R)
+    filtered = L1_RANK_FILTER if filtered is None else filtered
+    nR = R.shape[0]
     with torch.cuda.device(R.device):
+        if filtered and nR < (1 << 31):
+            chunk = max(128, min(65535 * 128, FILTER_PAIRS_PER_CALL // max(nR, 1)) // 128 * 128)
+            ws = None
+            for c0 in range(0, L_block.shape[0], chunk):
+                blk = L_block[c0:c0 + chunk]
+                nb = int(lib.eg_l1_rank_filtered_workspace_bytes(blk.shape[0], nR))
+                if ws is None or ws.numel() < nb:
+                    ws = torch.empty(nb, dtype=torch.uint8, device=R.device)
+                check(lib.eg_l1_rank_filtered(ptr(blk), blk.shape[0], row0 + c0, ptr(R), nR, R.shape[1], ptr(diag),
+                                              ptr(rank_row), ptr(rank_col), ptr(ws), ws.numel(), stream()),
+                      "eg_l1_rank_filtered")
+            return
         for c0 in range(0, L_block.shape[0], FUSED_ROW_CHUNK):
             blk = L_block[c0:c0 + FUSED_ROW_CHUNK]
             check(lib.eg_l1_rank_fused(ptr(blk), blk.shape[0], row0 + c0, ptr(R), R.shape[0], R.shape[1], ptr(diag),
                                        ptr(rank_row), ptr(rank_col), stream()), "eg_l1_rank_fused")
 
 
-def l1_ranks(L, R, block_bytes=None, streamed=True):
+def l1_ranks(L, R, block_bytes=None, streamed=True, filtered=None):
     """Ranks of the diagonal (true match) per row and per column of the fp64 L1
     matrix between L and R (same length).  ``streamed=False`` takes the two-kernel route through a stored
-    distance block (kept for cross-checking; bit-identical)."""
+    distance block (kept for cross-checking; bit-identical); ``filtered`` picks the fp32-filter kernel (default)
+    or the all-fp64 streamed kernel — identical ranks."""
     n = L.shape[0]
     dev = L.device
     diag = l1_paired(L, R)
     rank_row = torch.zeros(n, dtype=torch.int32, device=dev)
     rank_col = torch.zeros(n, dtype=torch.int32, device=dev)
     if streamed:
-        l1_rank_fused(L, 0, R, diag, rank_row, rank_col)
+        l1_rank_fused(L, 0, R, diag, rank_row, rank_col, filtered=filtered)
         return rank_row, rank_col
     rows = l1_block_rows(n, block_bytes)
     buf = torch.empty(min(rows, n), n, dtype=torch.float64, device=dev)
@@ -377,11 +396,13 @@ def gemm_tn(a_split, m, b_split, n):
     return out
 
 
-def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False):
+def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False, sign_safe_cols=0):
     """C = [A1 | A2 ...] · Bᵀ + bias with fp32 accuracy (3xTF32 on tcgen05).
     A_parts: one or two [m, k_i] fp32 CUDA tensors; B: [n, sum k_i] fp32 (row j = output column j).
     Returns out1 [m, n1] (and out2 [m, n - n1] when n1 < n).  ``a_splits``: reuse hi/lo pairs computed earlier
-    (one per A part, padded to 16 columns); ``return_splits=True`` appends the list of pairs used."""
+    (one per A part, padded to 16 columns); ``return_splits=True`` appends the list of pairs used.
+    ``sign_safe_cols`` = c > 0: outputs in columns [0, c) feed a ReLU — those within the 3xTF32 error bound of zero
+    are re-evaluated in fp32 inside the kernel (eg_gemm_nt_3xtf32_signsafe), single A part only."""
     A_parts = [_f32c(a) for a in A_parts]
     if not 1 <= len(A_parts) <= 2:
         raise ValueError("gemm_nt takes one or two A operands")
@@ -410,10 +431,20 @@ def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False):
     a2_hi, a2_lo = (splits[1] if len(splits) == 2 else (None, None))
     bias = _f32c(bias) if bias is not None else None
     with torch.cuda.device(dev):
-        check(lib.eg_gemm_nt_3xtf32(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
-                                    _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
-                                    ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
-              "eg_gemm_nt_3xtf32")
+        if sign_safe_cols:
+            if len(ks) != 1:
+                raise ValueError("gemm_nt: sign_safe_cols needs a single A operand")
+            norm_a, norm_b = row_norms(A_parts[0], squared=False), row_norms(B, squared=False)
+            check(lib.eg_gemm_nt_3xtf32_signsafe(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), m, ptr(b_hi),
+                                                 ptr(b_lo), n, ptr(bias), ptr(out1), n1, n1, ptr(out2),
+                                                 (n - n1) if out2 is not None else 0, ptr(A_parts[0]), ptr(B), ks[0],
+                                                 ptr(norm_a), ptr(norm_b), int(sign_safe_cols), stream()),
+                  "eg_gemm_nt_3xtf32_signsafe")
+        else:
+            check(lib.eg_gemm_nt_3xtf32(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
+                                        _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
+                                        ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
+                  "eg_gemm_nt_3xtf32")
     res = (out1, out2) if out2 is not None else out1
     return (res, splits) if return_splits else res
 

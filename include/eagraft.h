@@ -151,6 +151,15 @@ int eg_topk_rows(const double* D, int64_t ldD, int64_t n_rows, int64_t n_cols,
  * eg_l1_topk_fused == eg_l1_matrix + eg_topk_rows for skip + k <= 128. */
 int eg_l1_rank_fused(const float* L, int64_t nL, int64_t row0, const float* R, int64_t nR, int d,
                      const double* diag, int32_t* rank_row, int32_t* rank_col, eg_stream_t stream);
+/* eg_l1_rank_fused with the distance tiles on the FP32 pipe as a CANDIDATE FILTER (utils/eval_utils.py:74-89):
+ * fl32 sums decide every comparison whose outcome is certain under the rounding bound (d + 2) * 2^-24; the pairs
+ * inside the band are re-evaluated exactly in fp64 (SciPy's summation order) by a second kernel, so ranks are
+ * identical to eg_l1_rank_fused.  If the candidate queue overflows (tie-heavy data) the exact kernel runs
+ * instead — decided on the device; the call never synchronises.  nR < 2^31. */
+size_t eg_l1_rank_filtered_workspace_bytes(int64_t nL, int64_t nR);
+int eg_l1_rank_filtered(const float* L, int64_t nL, int64_t row0, const float* R, int64_t nR, int d,
+                        const double* diag, int32_t* rank_row, int32_t* rank_col, void* ws, size_t ws_bytes,
+                        eg_stream_t stream);
 size_t eg_l1_topk_fused_workspace_bytes(int64_t nL, int64_t nR, int skip, int k);
 int eg_l1_topk_fused(const float* L, int64_t nL, const float* R, int64_t nR, int d, int skip, int k,
                      void* ws, size_t ws_bytes, int64_t* out_idx, eg_stream_t stream);
@@ -187,6 +196,12 @@ int eg_sinkhorn_dense(int dtype, const void* M, int64_t n_rows, int64_t n_cols, 
                       void* Mt, void* log_u, void* log_v, void* ws, size_t ws_bytes,
                       int* h_sweeps, double* h_err, eg_stream_t stream);
 size_t eg_sinkhorn_dense_workspace_bytes(int dtype, int64_t n_rows, int64_t n_cols);
+/* Measurement aid: `iters` repetitions of the per-sweep EXCHANGE of the one-launch fp32 solver with no mat-vec
+ * work (column partials through global memory + one grid barrier + partial reads, row partials through
+ * distributed shared memory + one cluster barrier), same launch shape as the solve of an n_rows x n_cols problem;
+ * ws as for eg_sinkhorn_dense(dtype 0).  Timed by the caller: the latency floor bench.py reports next to the
+ * measured sweep time.  EG_ERR_UNSUPPORTED when the tile kernel does not take this shape. */
+int eg_sinkhorn_sync_floor(int64_t n_rows, int64_t n_cols, int iters, void* ws, size_t ws_bytes, eg_stream_t stream);
 
 /* FUSED half-sweep: the cost tile is recomputed from the two embedding sets and
  * reduced straight into the row log-sum-exp; M is never written
@@ -228,6 +243,17 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
                       const float* A2_hi, const float* A2_lo, int k2_pad, int64_t m,
                       const float* B_hi, const float* B_lo, int64_t n, const float* bias,
                       float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
+
+/* The same product with a sign-safe epilogue for the columns that feed a ReLU (layers/layers.py:32-38, 61-67:
+ * act(A·(x Wᵀ + b))): an output in columns [0, safe_cols) whose magnitude is below the 3xTF32 error bound
+ * 4e-6 * |a_i| * |b_j| (normA[m], normB[n]: Euclidean row norms, eg_row_norms with squared = 0) is re-evaluated as
+ * a plain fp32 dot product of the raw rows A_raw[m, k], B_raw[n, k] (contiguous), so the ReLU mask is the one an
+ * fp32 GEMM produces.  Single A operand. */
+int eg_gemm_nt_3xtf32_signsafe(const float* A_hi, const float* A_lo, int k_pad, int64_t m,
+                               const float* B_hi, const float* B_lo, int64_t n, const float* bias,
+                               float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2,
+                               const float* A_raw, const float* B_raw, int k,
+                               const float* normA, const float* normB, int64_t safe_cols, eg_stream_t stream);
 
 /* Weight gradient of those products: C[m, n] = sum_k A[k, m] * B[k, n]  (dW = dH^T x; K = #entities).
  * A, B are the SAME row-major hi/lo split arrays ([K, lda], [K, ldb], lda/ldb % 4 == 0, 16-byte aligned) that

@@ -283,12 +283,46 @@ def test_streamed_topk_and_ranks_with_ties(nL, nR, d, skip, k, dev):
     assert np.array_equal(got[sub], want)
     n = min(nL, nR)
     if n > 1:
-        rs, cs = ops.l1_ranks(Lg[:n], Rg[:n], streamed=True)
+        rs, cs = ops.l1_ranks(Lg[:n], Rg[:n], streamed=True)                 # fp32 filter (queue overflows here:
+        rx, cx = ops.l1_ranks(Lg[:n], Rg[:n], streamed=True, filtered=False)  # tie-heavy data) vs all-fp64 streamed
         rm, cm = ops.l1_ranks(Lg[:n], Rg[:n], streamed=False)
         assert torch.equal(rs, rm) and torch.equal(cs, cm)
+        assert torch.equal(rx, rm) and torch.equal(cx, cm)
         if n <= 3000:
             rr, cr = orc.diagonal_ranks(orc.l1_matrix(L[:n], R[:n]))
             assert np.array_equal(rs.cpu().numpy(), rr) and np.array_equal(cs.cpu().numpy(), cr)
+
+
+@pytest.mark.parametrize("n,d,noise", [(1, 300, 0.5), (130, 7, 0.5), (3000, 300, 0.05), (5000, 300, 3.0),
+                                       (4097, 129, 1.0), (10500, 300, 0.5)])
+def test_rank_filter_identical_to_exact(n, d, noise, dev):
+    """fp32 candidate filter + exact fp64 decisions == all-fp64 kernels, on continuous data (near-ties only inside
+    the rounding band), with duplicated rows / columns (exact ties), row blocks offset by row0, and through the
+    sharded-row entry (row0 > 0)."""
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import ops
+    rng = np.random.default_rng(n + d)
+    L = rng.standard_normal((n, d)).astype(np.float32)
+    R = (L + noise * rng.standard_normal((n, d))).astype(np.float32)
+    if n > 200:
+        R[100:110] = R[90:100]
+        L[120:125] = L[130:135]
+        R[150] = L[150]                      # zero distance on the diagonal
+    Lg, Rg = torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)
+    rf, cf = ops.l1_ranks(Lg, Rg, filtered=True)
+    rx, cx = ops.l1_ranks(Lg, Rg, filtered=False)
+    assert torch.equal(rf, rx) and torch.equal(cf, cx)
+    if n <= 5000:
+        rr, cr = orc.diagonal_ranks(orc.l1_matrix(L, R))
+        assert np.array_equal(rf.cpu().numpy(), rr) and np.array_equal(cf.cpu().numpy(), cr)
+    if n >= 3000:                            # two row blocks, as the sharded evaluation calls it
+        diag = ops.l1_paired(Lg, Rg)
+        r2 = torch.zeros(n, dtype=torch.int32, device=dev)
+        c2 = torch.zeros(n, dtype=torch.int32, device=dev)
+        cut = n // 3 + 5
+        ops.l1_rank_fused(Lg[:cut], 0, Rg, diag, r2, c2, filtered=True)
+        ops.l1_rank_fused(Lg[cut:], cut, Rg, diag, r2, c2, filtered=True)
+        assert torch.equal(r2, rx) and torch.equal(c2, cx)
 
 
 # ------------------------------------------------------------------- sinkhorn --

@@ -168,7 +168,61 @@ def _w_overlapped_gather(rank, world):
     assert torch.allclose(got, M @ H, atol=1e-5)
 
 
+def _w_sharded_neg_and_pairs(rank, world):
+    """get_neg / generate_pairs with rows split over ranks == the oracle's single-process result, incl. exact ties
+    (duplicated embeddings) where the lowest index must win on every rank."""
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import parallel as par
+    rng = np.random.default_rng(11)
+    e1, e2, d = 23, 19, 4
+    x = (rng.integers(-2, 3, (e1 + e2, d)) * 0.5).astype(np.float32)       # coarse grid: many tied distances
+    x[e1 + 3] = x[e1 + 7]
+    x[5] = x[9]
+    out = torch.from_numpy(x)
+
+    def topk_fn(A, B, skip, k):
+        D = torch.from_numpy(orc.l1_matrix(A.numpy(), B.numpy()))
+        return torch.argsort(D, dim=1, stable=True)[:, skip:skip + k]
+
+    def argmins_fn(Lr, Rr):
+        D = orc.l1_matrix(Lr.numpy(), Rr.numpy())
+        return (torch.from_numpy(D.min(1)), torch.from_numpy(D.argmin(1)), torch.from_numpy(D.min(0)),
+                torch.from_numpy(D.argmin(0)))
+    anchors = np.array([0, 5, 9, 22, 30, 41, 7], dtype=np.int64)
+    got = par.get_neg_sharded(anchors, out, 6, topk_fn=topk_fn)
+    assert np.array_equal(got, orc.nearest_negatives(anchors, out, 6))
+    data = {"e1": e1, "e2": e2, "index1": np.arange(e1), "index2": np.arange(e2) + e1}
+    pairs = par.generate_pairs_sharded(out, data, 10, argmins_fn=argmins_fn)
+    want = orc.mutual_nearest_pairs(out, data["index1"], data["index2"], 10)
+    assert np.array_equal(pairs, want), (pairs, want)
+    # merge rule on its own: equal minima on both ranks -> the lower row index wins
+    v = torch.tensor([1.0, 2.0 + rank, 0.5], dtype=torch.float64)
+    a = torch.tensor([10 + rank, 3 - rank, 7 * (1 - rank) + 2], dtype=torch.int64)
+    m, arg = par.merge_col_argmin(v, a)
+    assert m.tolist() == [1.0, 2.0, 0.5] and arg.tolist() == [10, 3, 2]
+
+
+def _w_overlapped_grad_sync(rank, world):
+    from gnn_mtl_b200 import parallel as par
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.ReLU(), torch.nn.Linear(4, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.ReLU(), torch.nn.Linear(4, 3))
+    ref.load_state_dict(net.state_dict())
+    xs = [torch.randn(6, 5, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    sync = par.OverlappedGradSync(net.parameters())
+    for step in range(2):
+        net.zero_grad()
+        net(xs[rank]).square().sum().backward()
+        sync.finish()
+        ref.zero_grad()
+        for r in range(world):
+            (ref(xs[r]).square().sum() / world).backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), step
+    sync.remove()
+
+
 @pytest.mark.parametrize("worker", [_w_sinkhorn, _w_gather_and_grads, _w_rank_merge, _w_sharded_adjacency,
-                                    _w_overlapped_gather])
+                                    _w_overlapped_gather, _w_sharded_neg_and_pairs, _w_overlapped_grad_sync])
 def test_world2_gloo(worker):
     _run(worker, 2)
