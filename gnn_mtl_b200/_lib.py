@@ -57,6 +57,8 @@ SIGNATURES = {
     "eg_split_tf32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "eg_plan_fused": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp]),
+    "eg_plan_grad_fused_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "eg_plan_grad_fused": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _f32, _vp, _sz, _vp, _vp]),
     "eg_gemm_nt_3xtf32": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp,
                                     _i64, _vp]),
     "eg_gemm_nt_3xtf32_signsafe": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64,

@@ -1346,11 +1346,15 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
               const PersistState& fin = hs[0].sweeps < kWarmSweeps ? hs[0] : (hs[1].fallback ? hs[2] : hs[1]);
               if (h_sweeps) *h_sweeps = fin.sweeps;
               if (h_err) *h_err = fin.err;
-              if (timing && hs[1].sweeps > kWarmSweeps) {
-                const double n = hs[1].sweeps - kWarmSweeps;
-                fprintf(stderr, "[eagraft] tile2d sinkhorn: %d sweeps, fallback %d; CTA0 us/sweep: C %.2f | barrier %.2f | v %.2f | U dots %.2f | exchange+u %.2f\n",
-                        hs[1].sweeps, hs[1].fallback, hs[1].t_phase[0] / 1e3 / n, hs[1].t_phase[1] / 1e3 / n,
-                        hs[1].t_phase[2] / 1e3 / n, hs[1].t_phase[3] / 1e3 / n, hs[1].t_phase[4] / 1e3 / n);
+              if (timing) {
+                const double n = std::max(1, hs[1].sweeps - kWarmSweeps);
+                fprintf(stderr, "[eagraft] tile2d sinkhorn: warm-up %d sweeps; %d sweeps, fallback %d, redo sweeps %d; CTA0 us/sweep: C %.2f | barrier %.2f | v %.2f | U dots %.2f | exchange+u %.2f\n",
+                        hs[0].sweeps, hs[1].sweeps, hs[1].fallback, hs[2].sweeps, hs[1].t_phase[0] / 1e3 / n,
+                        hs[1].t_phase[1] / 1e3 / n, hs[1].t_phase[2] / 1e3 / n, hs[1].t_phase[3] / 1e3 / n,
+                        hs[1].t_phase[4] / 1e3 / n);
+                if (hs[1].fallback >= 2)
+                  fprintf(stderr, "[eagraft] tile2d barrier timeout: CTA %llu saw %llu arrivals, waited for %llu\n",
+                          hs[1].t_phase[6] >> 32, hs[1].t_phase[6] & 0xffffffffull, hs[1].t_phase[7]);
               }
             } else {
               // every sweep runs and nothing is read back: the whole solve stays asynchronous

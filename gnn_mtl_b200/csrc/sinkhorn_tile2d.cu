@@ -91,9 +91,10 @@ __device__ __forceinline__ double ld_relaxed_f64(const double* p) {
   return v;
 }
 
-// Grid barrier on a monotonically increasing counter (all CTAs co-resident: cooperative launch).  The wait is
-// bounded: after ~1 s without progress the CTA raises `fallback = 2` and goes on, every other waiter sees the flag
-// and goes on too — the solve is then redone by the log-domain kernel instead of hanging the device.
+// Grid barrier on a monotonically increasing counter (all CTAs co-resident: verified once per device by
+// t2_probe_kernel, and the launch is cooperative).  The wait is bounded: after 20 ms without progress (a sweep
+// takes microseconds) the CTA raises the sticky `fallback = 2`, every waiter sees it and leaves its sweep loop at
+// the next check — the solve is then redone by the log-domain kernel instead of hanging the device.
 __device__ __forceinline__ void t2_grid_barrier(PersistState* st, unsigned int& target, unsigned int nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -105,10 +106,13 @@ __device__ __forceinline__ void t2_grid_barrier(PersistState* st, unsigned int& 
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->barrier) : "memory");
       if ((int)(seen - target) >= 0) break;
-      if ((++spins & 1023u) == 0) {
-        if (ld_relaxed_s32(&st->fallback) == 2) break;
-        if (gtime() - t0 > 1000000000ull) {
-          atomicExch(&st->fallback, 2);
+      if ((++spins & 255u) == 0 || spins == 1) {
+        if (ld_relaxed_s32(&st->fallback) >= 2) break;   // aborted solve: nobody waits any more
+        if (gtime() - t0 > 20000000ull) {
+          if (atomicMax(&st->fallback, 2) < 2) {         // first to give up: leave a trace for EG_PERSIST_TIMING
+            st->t_phase[6] = ((unsigned long long)blockIdx.x << 32) | seen;
+            st->t_phase[7] = target;
+          }
           atomicMax(&st->flag_code, 0x7fffffff);       // "raised before every sweep": acted on at once
           break;
         }
@@ -333,7 +337,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
           v_s[tid] = vn;
         }
       }
-      if (check && p == 0 && tid < nc4) {
+      if (check && p == 0) {                 // CTA-uniform: every lane of every warp takes part (d2 = 0 past nc4)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
         if (lane == 0 && d2 != 0.0) atomicAdd(&st->err2[slot], d2);
@@ -361,7 +365,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       if (brk == 1) break;
       if (brk == 2) { stop_hit = true; break; }
       if (flag_s[2] && tid == 0) {
-        atomicExch(&st->fallback, 1);
+        atomicMax(&st->fallback, 1);
         atomicMax(&st->flag_code, 0x7fffffff - cpt);
       }
       if (check) { pending_slot = slot; pending_cpt = cpt; }
@@ -456,12 +460,12 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   }
   // a check issued in the very last sweep: its sum is complete one barrier later
   if (cpt >= P.max_iter && pending_slot >= 0) {
-    if (flag_s[2] && tid == 0) { atomicExch(&st->fallback, 1); }
+    if (flag_s[2] && tid == 0) { atomicMax(&st->fallback, 1); }
     t2_grid_barrier(st, target, nb);
     err = sqrt(ld_relaxed_f64(&st->err2[pending_slot]));
     if (!(err > P.stop_thr)) stop_hit = true;
   } else if (cpt >= P.max_iter) {
-    if (flag_s[2] && tid == 0) atomicExch(&st->fallback, 1);     // last sweep's sums: no later barrier publishes them
+    if (flag_s[2] && tid == 0) atomicMax(&st->fallback, 1);     // last sweep's sums: no later barrier publishes them
   }
   __syncthreads();
   // ---- outputs (natural-log potentials, composed in fp64) ------------------------------------------------------
@@ -482,7 +486,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
     st->sweeps = stop_hit ? pending_cpt : sweeps;
     st->final_buf = 0;
     st->err = err;
-    if (P.force_fallback) st->fallback = 1;
+    if (P.force_fallback) atomicMax(&st->fallback, 1);
   }
 }
 
@@ -546,15 +550,88 @@ int sinkhorn_tile2d_absorbs_read() {
   return v;
 }
 
+// Co-residency probe: the same launch shape (cluster of 8, 512 threads, the solver's dynamic shared memory) doing
+// ONE grid barrier with a 5 ms budget.  If some cluster cannot be resident together with the others the barrier
+// times out and *ok is cleared — the occupancy query is a necessary condition, this is the sufficient one.
+__global__ void __launch_bounds__(kT2Threads, 1)
+t2_probe_kernel(unsigned int* counter, int* ok, unsigned int nblocks) {
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1u);
+    const unsigned long long t0 = gtime();
+    for (;;) {
+      unsigned int seen;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen >= nblocks) break;
+      if (gtime() - t0 > 5000000ull) { atomicExch(ok, 0); break; }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+}
+
 // Launch geometry: the fewest rows per warp for which the co-resident clusters cover all rows.
 struct T2Geometry { int nc, nrw, gs, rows_per_cluster; size_t smem; };
-template <typename Kern>
-static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, T2Geometry* g, cudaLaunchConfig_t* cfg,
-                       cudaLaunchAttribute* attrs) {
-  g->nc = 0;
+
+// Clusters of 8 CTAs (one CTA per SM at the largest shared-memory request) that were SEEN running together on this
+// device: starts from the occupancy query and walks down until the probe's grid barrier completes.  One-time host
+// synchronisation per device; 0 = unknown, -1 = clusters unusable.
+static std::atomic<int> g_t2_verified_clusters[64];
+static int t2_verified_clusters(PersistState* scratch, cudaStream_t s, int* out) {
   int dev = 0, max_smem = 0;
   EG_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { *out = 0; return EG_OK; }
+  int cached = g_t2_verified_clusters[dev].load(std::memory_order_acquire);
+  if (cached != 0) { *out = std::max(cached, 0); return EG_OK; }
   EG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  auto kern = t2_probe_kernel;
+  const size_t smem = (size_t)max_smem - 1024;
+  EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kT2CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kT2Threads);
+  cfg.stream = s;
+  cfg.attrs = attrs;
+  cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(kT2CS * kT2MaxClusters);
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  n = std::min(n, kT2MaxClusters);
+  int verified = -1;
+  for (; n >= 4; --n) {
+    EG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(PersistState), s));
+    int one = 1;
+    EG_CUDA(cudaMemcpyAsync(&scratch->sweeps, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    cfg.gridDim = dim3((unsigned)(kT2CS * n));
+    cfg.numAttrs = 2;
+    unsigned int nblocks = (unsigned)(kT2CS * n);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, &scratch->barrier, &scratch->sweeps, nblocks);
+    if (e != cudaSuccess) { cudaGetLastError(); continue; }          // cooperative launch refused: too many clusters
+    int ok = 0;
+    EG_CUDA(cudaMemcpyAsync(&ok, &scratch->sweeps, sizeof(int), cudaMemcpyDeviceToHost, s));
+    EG_CUDA(cudaStreamSynchronize(s));
+    if (getenv("EG_PERSIST_TIMING")) fprintf(stderr, "[eagraft] cluster probe: %d clusters of %d -> %s\n", n, kT2CS, ok ? "co-resident" : "NOT co-resident");
+    if (ok) { verified = n; break; }
+  }
+  g_t2_verified_clusters[dev].store(verified, std::memory_order_release);
+  *out = std::max(verified, 0);
+  return EG_OK;
+}
+
+template <typename Kern>
+static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, PersistState* scratch, T2Geometry* g,
+                       cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs) {
+  g->nc = 0;
+  int dev = 0, max_smem = 0, verified = 0;
+  EG_CUDA(cudaGetDevice(&dev));
+  EG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int vrc = t2_verified_clusters(scratch, s, &verified);
+  if (vrc) return vrc;
+  if (verified < 4) return EG_OK;
   g->gs = (int)ceil_div(J / 4, (int64_t)kT2CS);
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kT2CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
@@ -573,7 +650,7 @@ static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, T2Geomet
     cfg->numAttrs = 1;
     int max_clusters = 0;
     if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg) != cudaSuccess) { cudaGetLastError(); return EG_OK; }
-    max_clusters = std::min(max_clusters, kT2MaxClusters);
+    max_clusters = std::min(std::min(max_clusters, kT2MaxClusters), verified);
     if (max_clusters < 4) continue;
     if ((int64_t)max_clusters * kT2Warps * try_nrw >= I) {
       g->nrw = try_nrw;
@@ -598,17 +675,12 @@ int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* pa
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attrs[2];
   auto kern = sinkhorn_tile2d_sync_floor_kernel;
-  int rc = t2_geometry(kern, I, J, s, &g, &cfg, attrs);
+  int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
   if (g.nc == 0 || (size_t)2 * kT2CS * g.nc * g.gs * 4 > part_floats) return EG_OK;
   EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, part, g.nc, g.gs, g.nrw, iters);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, st, part, g.nc, g.gs, g.nrw, iters);
-    if (e != cudaSuccess) { cudaGetLastError(); return EG_OK; }
-  }
+  if (e != cudaSuccess) { cudaGetLastError(); return EG_OK; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   *launched = true;
   return EG_OK;
@@ -624,9 +696,10 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attrs[2];
   auto kern = sinkhorn_tile2d_kernel;
-  int rc = t2_geometry(kern, I, J, s, &g, &cfg, attrs);
+  int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
   if (g.nc == 0 || (size_t)2 * kT2CS * g.nc * g.gs * 4 > part_floats) return EG_OK;
+  EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));      // the probe may have used it
   T2Params P;
   P.M = M; P.I = I; P.J = (int)J; P.ld = ld; P.inv2 = inv_reg * 1.4426950408889634074;
   P.a = a; P.b = b; P.log_u = log_u; P.log_v = log_v;
@@ -634,13 +707,10 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
   P.nc = g.nc; P.rows_per_cluster = g.rows_per_cluster; P.nrw = g.nrw; P.gs = g.gs; P.absorb_log2 = absorb_log2;
   P.force_fallback = force_fallback;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
-  if (e != cudaSuccess) {
-    // cooperative + cluster refused by this driver: the occupancy query above already guarantees that the whole
-    // grid is co-resident on an otherwise idle device, and the barrier waits are bounded
+  if (e != cudaSuccess) {          // cooperative + cluster launch refused: the caller takes the row-block kernel
     cudaGetLastError();
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, P);
-    if (e != cudaSuccess) { cudaGetLastError(); return EG_OK; }
+    if (getenv("EG_PERSIST_TIMING")) fprintf(stderr, "[eagraft] tile2d launch refused: %s\n", cudaGetErrorString(e));
+    return EG_OK;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (getenv("EG_PERSIST_TIMING"))

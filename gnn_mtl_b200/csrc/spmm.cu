@@ -21,6 +21,8 @@ constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
 int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each)
 int g_tune_warps = 4;       // warps (= rows) per CTA
 int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelined SpMM with n CTAs per SM
+int g_tune_spmm_slab = 0;   // eg_debug_set(14, v): v in {32, 64}: walk the feature columns in slabs of v float4 (one launch
+                            // per slab, rows inner) so that a slab of H stays L2-resident; 0: as wide as the kernel allows
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
 
 struct Epilogue {
@@ -439,6 +441,7 @@ int eg_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t
     int d4 = d / 4;
     for (int chunk0 = 0; chunk0 < d4;) {
       int rem = d4 - chunk0;
+      if (g_tune_spmm_slab == 32 || g_tune_spmm_slab == 64) rem = std::min(rem, g_tune_spmm_slab);
       int rc;
       if (rem <= 32) { rc = launch_vec<1>(rowptr, col, val, n_rows, H, d4, chunk0, ep, long_row_threshold, seg_begin, seg_end, n_seg, seg_scratch, s); chunk0 += 32; }
       else if (rem <= 64) { rc = launch_vec<2>(rowptr, col, val, n_rows, H, d4, chunk0, ep, long_row_threshold, seg_begin, seg_end, n_seg, seg_scratch, s); chunk0 += 64; }

@@ -373,6 +373,19 @@ def plan_fused(A, B, cost, inv_reg, f, g, want_plan=False, want_rows=True, algo=
     return P, loss[0], rs
 
 
+def plan_grad_fused(A, B, cost, inv_reg, f, g, scale=1.0):
+    """dA = scale * sum_j P_ij d cost(A_i, B_j)/dA_i with P = exp(f_i + g_j - cost/reg); A, B FusedOperand."""
+    dev = A.X.device
+    dA = torch.empty_like(A.X)
+    with torch.cuda.device(dev):
+        nb = int(lib.eg_plan_grad_fused_workspace_bytes(A.n, B.n, A.d))
+        ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
+        check(lib.eg_plan_grad_fused(cost, ptr(A.X), A.n, ptr(B.X), B.n, A.d, ptr(A.norm), ptr(B.norm), float(inv_reg),
+                                     ptr(f), ptr(g), float(scale), ptr(ws), ws.numel(), ptr(dA), stream()),
+              "eg_plan_grad_fused")
+    return dA
+
+
 # ---- dense layer products on the tcgen05 3xTF32 tiles -----------------------------------------
 
 def _pad16(k):

@@ -78,3 +78,37 @@ def sinkhorn_fused(X, Y, a, b, reg, numItermax=1000, stopThr=1e-9, cost="l2", al
     if info is not None:
         info.update(sweeps=sweeps, err=err, log_u=log_u, log_v=log_v)
     return P, loss
+
+
+class _FusedOTLoss(torch.autograd.Function):
+    """<P, C(X, Y)> with P the Sinkhorn plan of the detached cost — the differentiable form of
+    models/models_ea.py:218-224 (``sinkhorn(a, b, M.detach(), reg)`` then ``sum(T * M)``) without ever storing
+    M or T: forward = the fused tcgen05 solve, backward = one streamed pass per operand (eg_plan_grad_fused)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, a, b, reg, numItermax, stopThr, cost, algo):
+        info = {}
+        _, loss = sinkhorn_fused(X, Y, a, b, reg, numItermax=numItermax, stopThr=stopThr, cost=cost, algo=algo,
+                                 return_plan=False, info=info)
+        ctx.save_for_backward(X.detach(), Y.detach(), info["log_u"], info["log_v"])
+        ctx.reg, ctx.cost = float(reg), cost
+        ctx.sweeps = info["sweeps"]
+        return loss.to(torch.float32) if X.dtype == torch.float32 else loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        X, Y, log_u, log_v = ctx.saved_tensors
+        cost_id = {"l2": _lib.COST_L2, "sqeuclid": _lib.COST_SQEUCLID, "cos": _lib.COST_COSINE}[ctx.cost]
+        A = ops.FusedOperand(X, cost_id, _lib.ALGO_SIMT)
+        B = ops.FusedOperand(Y, cost_id, _lib.ALGO_SIMT)
+        gout = gout.to(torch.float32)               # stays on the device: no host synchronisation
+        dX = ops.plan_grad_fused(A, B, cost_id, 1.0 / ctx.reg, log_u, log_v).mul_(gout) if ctx.needs_input_grad[0] else None
+        dY = ops.plan_grad_fused(B, A, cost_id, 1.0 / ctx.reg, log_v, log_u).mul_(gout) if ctx.needs_input_grad[1] else None
+        return dX, dY, None, None, None, None, None, None, None
+
+
+def sinkhorn_fused_loss(X, Y, a, b, reg, numItermax=1000, stopThr=1e-9, cost="l2", algo="tcgen05"):
+    """Differentiable OT loss sum_ij T_ij cost(X_i, Y_j), T = sinkhorn(a, b, cost.detach(), reg): what
+    ``get_loss_wassertein`` computes before its argmax-of-zeros quirk (models/models_ea.py:218-224), with the cost
+    recomputed tile by tile in both passes.  Gradients flow to X and Y through the cost only, as in the reference."""
+    return _FusedOTLoss.apply(X, Y, a, b, reg, numItermax, stopThr, cost, algo)

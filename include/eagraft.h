@@ -58,7 +58,8 @@ void eg_launch_count_reset(void);
  *   set (returns EG_OK):  0/1 SpMM rows-in-flight / warps per CTA, 2 SpMM L2 hints, 3 persistent Sinkhorn on/off,
  *     4 resident rows on/off, 5 on-chip fp32 Sinkhorn on/off, 6 persistent SpMM CTAs per SM, 7 scaling-domain
  *     continuation on/off, 10 fold threshold (|log2| x 1000), 11 force the log-domain redo, 12 2-D tiled scaling
- *     kernel on/off (off: row-block kernel), 13 fp32 candidate filter of the L1 rank kernels on/off
+ *     kernel on/off (off: row-block kernel), 13 fp32 candidate filter of the L1 rank kernels on/off, 14 SpMM feature
+ *     slab width in float4 (0 / 32 / 64)
  *   query (value ignored): 8 scaling-domain solves redone in the log domain so far, 9 fold steps so far
  * Queries 8/9 read device counters and synchronise the device. */
 int eg_debug_set(int key, int value);
@@ -231,6 +232,17 @@ int eg_plan_fused(int algo, int cost, const float* A, int64_t nA, const float* B
                   const float* f, const float* g, float* P, int64_t ldP, double* loss, float* row_sum,
                   const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
                   eg_stream_t stream);
+
+/* Backward of the fused OT loss with the plan held fixed (models/models_ea.py:218-224: sinkhorn() is called on
+ * M.detach(), the gradient flows through the cost only):
+ *     dA[i, :] = scale * sum_j P_ij * d cost(A_i, B_j) / d A_i ,   P_ij = exp(f[i] + g[j] - cost_ij * inv_reg)
+ * streamed over 64 x 64 tiles — neither the cost nor the plan is stored.  normA / normB as for eg_lse_fused
+ * (squared norms for the L2 costs, norms for cosine).  d <= 320.  dB is the same call with (A, f) and (B, g)
+ * exchanged.  Deterministic (partials summed in a fixed order). */
+size_t eg_plan_grad_fused_workspace_bytes(int64_t nA, int64_t nB, int d);
+int eg_plan_grad_fused(int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,
+                       const float* normA, const float* normB, float inv_reg, const float* f, const float* g,
+                       float scale, void* ws, size_t ws_bytes, float* dA, eg_stream_t stream);
 
 /* ---- dense products of the layers on the same tcgen05 3xTF32 tiles ----------------
  * C[m, n] = [A1 | A2][m, k1+k2] · B[n, k1+k2]ᵀ + bias[n]   (fp32 accuracy, fp32 in/out)

@@ -394,6 +394,32 @@ def test_sinkhorn_fused_vs_oracle(cost, reg, algo, dev):
     assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < REL
 
 
+@pytest.mark.parametrize("cost,reg", [("l2", 0.05), ("sqeuclid", 0.1), ("cos", 0.02)])
+@pytest.mark.parametrize("I,J,d", [(200, 180, 300), (333, 1030, 128), (70, 65, 37)])
+def test_fused_ot_loss_is_differentiable(cost, reg, I, J, d, dev):
+    """sinkhorn_fused_loss: value and gradients (through the cost only, plan detached — models/models_ea.py:218-224)
+    against fp64 autograd on the materialised cost with the oracle's plan; aligned pairs included (close-pair path)."""
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200.utils.ot_loss import sinkhorn_fused_loss
+    torch.manual_seed(I + d)
+    X = torch.randn(I, d) * 0.06
+    Y = torch.randn(J, d) * 0.06
+    Y[:40] = X[:40] + 0.004 * torch.randn(40, d)
+    a = torch.rand(I) + 0.5
+    b = torch.rand(J) + 0.5
+    b = b * a.sum() / b.sum()
+    Xd, Yd = X.double().requires_grad_(True), Y.double().requires_grad_(True)
+    M = {"l2": orc.cost_l2, "sqeuclid": orc.cost_sqeuclid, "cos": orc.cost_cosine}[cost](Xd, Yd)
+    P, _ = orc.sinkhorn_scaling(a, b, M.detach(), reg, numItermax=60, stopThr=-1.0)
+    loss_ref = (P * M).sum()
+    loss_ref.backward()
+    Xg, Yg = X.to(dev).requires_grad_(True), Y.to(dev).requires_grad_(True)
+    loss = sinkhorn_fused_loss(Xg, Yg, a.to(dev), b.to(dev), reg, numItermax=60, stopThr=-1.0, cost=cost)
+    (3.0 * loss).backward()
+    assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < REL
+    assert relerr(Xg.grad / 3.0, Xd.grad) < 5 * REL and relerr(Yg.grad / 3.0, Yd.grad) < 5 * REL
+
+
 @pytest.mark.parametrize("nA,nB,d", [(1, 1, 8), (129, 257, 300), (700, 1300, 128), (2500, 900, 52)])
 def test_fused_lse_tcgen05_matches_fp64(nA, nB, d, dev):
     """TMA + tcgen05 3xTF32 cost tiles against an fp64 materialised reference, ragged edges included."""
