@@ -1324,7 +1324,8 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
         // ---- default: warm-up -> 2-D tiled scaling kernel -> conditional redo, with NO host synchronisation unless
         // the caller's stop rule needs the sweep count / error back (stop_thr >= 0)
         bool warm_done = false;
-        if (g_tune_scaling && g_tune_tile2d && max_iter >= kWarmSweeps + 8) {
+        static const bool env_tile2d_off = getenv("EG_TILE2D") != nullptr && getenv("EG_TILE2D")[0] == '0';
+        if (g_tune_scaling && g_tune_tile2d && !env_tile2d_off && max_iter >= kWarmSweeps + 8) {
           int rc = launch_log(kWarmSweeps, w.state, nullptr);
           if (rc) return rc;
           EG_CUDA(cudaMemsetAsync(w.state2, 0, sizeof(PersistState), s));
