@@ -29,8 +29,7 @@ int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, c
 
 int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_hi, const float* A2_lo, int k2p,
                int64_t m, const float* B_hi, const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1,
-               int64_t n1, float* out2, int64_t ld2, const float* A_raw, const float* B_raw, int k_raw,
-               const float* normA, const float* normB, int64_t safe_cols, cudaStream_t s);
+               int64_t n1, float* out2, int64_t ld2, cudaStream_t s);
 
 constexpr int kFT = 64;    // tile edge
 constexpr int kFK = 16;    // k-chunk
@@ -354,19 +353,7 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad, const 
   if (!A1_hi || !A1_lo || !B_hi || !B_lo || !out1) return EG_ERR_INVALID;
   if (k2_pad > 0 && (!A2_hi || !A2_lo)) return EG_ERR_INVALID;
   return gemm_nt_tc(A1_hi, A1_lo, k1_pad, A2_hi, A2_lo, k2_pad, m, B_hi, B_lo, n, bias, out1, ld1, n1, out2, ld2,
-                    nullptr, nullptr, 0, nullptr, nullptr, 0, as_stream(stream_));
-}
-
-int eg_gemm_nt_3xtf32_signsafe(const float* A_hi, const float* A_lo, int k_pad, int64_t m, const float* B_hi,
-                               const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1, int64_t n1,
-                               float* out2, int64_t ld2, const float* A_raw, const float* B_raw, int k,
-                               const float* normA, const float* normB, int64_t safe_cols, eg_stream_t stream_) {
-  using namespace eg;
-  if (m < 0 || n <= 0) return EG_ERR_INVALID;
-  if (m == 0) return EG_OK;
-  if (!A_hi || !A_lo || !B_hi || !B_lo || !out1) return EG_ERR_INVALID;
-  return gemm_nt_tc(A_hi, A_lo, k_pad, nullptr, nullptr, 0, m, B_hi, B_lo, n, bias, out1, ld1, n1, out2, ld2, A_raw,
-                    B_raw, k, normA, normB, safe_cols, as_stream(stream_));
+                    as_stream(stream_));
 }
 
 int eg_plan_fused(int algo, int cost, const float* A, int64_t nA, const float* B, int64_t nB, int d,

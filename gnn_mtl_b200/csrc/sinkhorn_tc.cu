@@ -116,15 +116,7 @@ struct Params {
   float* out1;             // C[:, 0:n1)   row stride ld1          (MODE 2)
   float* out2;             // C[:, n1:nB)  row stride ld2          (MODE 2, nullable)
   int64_t ld1, ld2, n1;
-  int64_t safe_cols;       // MODE 2: outputs in columns [0, safe_cols) feed a ReLU — entries smaller than the 3xTF32
-                           // error bound kSignFrac * |a_i| * |b_j| are re-evaluated in fp32 from A_raw / B_raw
 };
-
-// 3xTF32 on tcgen05 is off by at most ~2e-6 * sum_k |a_k b_k| <= 2e-6 |a| |b| (the tensor core truncates on every
-// accumulate).  That is irrelevant except where the consumer is discontinuous: a pre-activation whose sign is not
-// certain under that bound is recomputed as a plain fp32 dot product (error ~1e-7 |a| |b|, what an fp32 GEMM gives),
-// so the ReLU mask — and with it every gradient entry behind it — is the one an fp32 product would produce.
-constexpr float kSignFrac = 4e-6f;
 
 // MODE 0: per-row online log-sum-exp of  pot_in[j] - cost*inv_reg          -> part_m / part_s
 // MODE 1: plan statistics with P_ij = exp(pot_a[i] + pot_in[j] - cost*inv_reg) -> loss, row_sum
@@ -257,7 +249,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       for (int c = ep_tid; c < BN; c += 128) {
         int64_t j = j0 + c;
         if (MODE == 2)
-          ci[c] = make_float2((j < p.safe_cols) ? p.normB[j] : 0.f, (j < p.nB && p.pot_in) ? p.pot_in[j] : 0.f);
+          ci[c] = make_float2(0.f, (j < p.nB && p.pot_in) ? p.pot_in[j] : 0.f);
         else
           ci[c] = (j < p.nB) ? make_float2(p.normB[j], p.pot_in[j]) : make_float2(0.f, -CUDART_INF_F);
       }
@@ -272,31 +264,6 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         if (MODE == 2) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) dot[c] += ci[c0 + c].y;
-          if (j0 + c0 < p.safe_cols) {            // uniform: this chunk holds ReLU-feeding columns
-            const float na_fix = (trow < p.nA) ? kSignFrac * p.normA[trow] : 0.f;
-            unsigned mine = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (fabsf(dot[c]) < na_fix * ci[c0 + c].x) mine |= 1u << c;     // normB = 0 outside [0, safe_cols)
-            unsigned owners = __ballot_sync(0xffffffffu, mine != 0);
-            while (owners) {
-              const int src = __ffs(owners) - 1;
-              owners &= owners - 1;
-              unsigned cols = __shfl_sync(0xffffffffu, mine, src);
-              const float* arow = p.A_raw + (tile_i0(t) + quad * 32 + src) * p.d;
-              while (cols) {
-                const int c = __ffs(cols) - 1;
-                cols &= cols - 1;
-                const float ex = exact_pair_warp(arow, p.B_raw + (j0 + c0 + c) * p.d, p.d, 1, lane);
-                if (lane == src) {
-                  const float fixed = ex + ci[c0 + c].y;
-#pragma unroll
-                  for (int cc = 0; cc < 32; ++cc)
-                    if (cc == c) dot[cc] = fixed;
-                }
-              }
-            }
-          }
           if (trow < p.nA) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
@@ -564,12 +531,8 @@ int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, c
 // splits (eg_split_tf32) with every K extent padded to a multiple of 16 (= one k-block).
 int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_hi, const float* A2_lo, int k2p,
                int64_t m, const float* B_hi, const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1,
-               int64_t n1, float* out2, int64_t ld2, const float* A_raw, const float* B_raw, int k_raw,
-               const float* normA, const float* normB, int64_t safe_cols, cudaStream_t s) {
+               int64_t n1, float* out2, int64_t ld2, cudaStream_t s) {
   using namespace tc;
-  if (safe_cols < 0 || safe_cols > n) return EG_ERR_INVALID;
-  if (safe_cols > 0 && (!A_raw || !B_raw || !normA || !normB || k_raw <= 0 || k2p != 0 || k_raw > k1p))
-    return EG_ERR_INVALID;
   if (k1p <= 0 || k1p % BK || k2p < 0 || k2p % BK || n % 4 || n1 % 4 || n1 > n || n1 <= 0) return EG_ERR_INVALID;
   if (n1 < n && !out2) return EG_ERR_INVALID;
   if (m >= (1ll << 31) || n >= (1ll << 31)) return EG_ERR_UNSUPPORTED;
@@ -597,7 +560,6 @@ int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_
   p.pot_in = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
   p.bn = bn;
   p.tiles_per_split = (int)ceil_div(n, (int64_t)bn);
-  p.safe_cols = safe_cols; p.A_raw = A_raw; p.B_raw = B_raw; p.d = k_raw; p.normA = normA; p.normB = normB;
   static PerDeviceOnce attr_once2;
   EG_SET_SMEM_ONCE(attr_once2,
                    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));

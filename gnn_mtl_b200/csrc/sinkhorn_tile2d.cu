@@ -102,13 +102,13 @@ __device__ __forceinline__ void t2_grid_barrier(PersistState* st, unsigned int& 
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->barrier) : "memory");
     unsigned int seen;
     unsigned int spins = 0;
-    const unsigned long long t0 = gtime();
+    const long long t0 = clock64();
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->barrier) : "memory");
       if ((int)(seen - target) >= 0) break;
-      if ((++spins & 255u) == 0 || spins == 1) {
+      if ((++spins & 63u) == 0) {
         if (ld_relaxed_s32(&st->fallback) >= 2) break;   // aborted solve: nobody waits any more
-        if (gtime() - t0 > 20000000ull) {
+        if (clock64() - t0 > 40000000ll) {               // ~20 ms of SM clocks
           if (atomicMax(&st->fallback, 2) < 2) {         // first to give up: leave a trace for EG_PERSIST_TIMING
             st->t_phase[6] = ((unsigned long long)blockIdx.x << 32) | seen;
             st->t_phase[7] = target;
@@ -311,16 +311,15 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       float s = 0.f;
       double d2 = 0.0;
       if (tid < nc4) {
+        // all partials requested before the first add (one L2 round trip, not NC of them); summed in cluster order
         const float* src = my_part + tid;
-        int pp = 0;
-        for (; pp + 8 <= NC; pp += 8) {
-          float t[8];
+        for (int pp = 0; pp < NC; pp += 16) {
+          float t[16];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) t[k] = ld_relaxed_f32(src + (size_t)(pp + k) * nc4);
+          for (int k = 0; k < 16; ++k) t[k] = (pp + k < NC) ? ld_relaxed_f32(src + (size_t)(pp + k) * nc4) : 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s += t[k];
+          for (int k = 0; k < 16; ++k) s += t[k];
         }
-        for (; pp < NC; ++pp) s += ld_relaxed_f32(src + (size_t)pp * nc4);
         const bool live = tid < ncols;
         const float v_old = v_s[tid];
         if (check) {
@@ -521,7 +520,13 @@ sinkhorn_tile2d_sync_floor_kernel(PersistState* st, float* part, int NC, int Gs,
     t2_grid_barrier(st, target, nb);
     if (tid < nc4) {
       float s = 0.f;
-      for (int pp = 0; pp < NC; ++pp) s += ld_relaxed_f32(my_part + (size_t)pp * nc4 + tid);
+      for (int pp = 0; pp < NC; pp += 16) {
+        float t[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t[k] = (pp + k < NC) ? ld_relaxed_f32(my_part + (size_t)(pp + k) * nc4 + tid) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s += t[k];
+      }
       v_s[tid] = 1.0f / s;
     }
     __syncthreads();

@@ -51,6 +51,10 @@ def classify_activation(act):
     return None
 
 
+# tests set this to a list to receive act(S) of every fused aggregation (to compare ReLU branch decisions)
+CAPTURE_ACT = None
+
+
 class _Aggregate(torch.autograd.Function):
     """out = epilogue(A · hidden);  backward: dH = Aᵀ · dS  (layers/layers.py:35,64 + autograd)."""
 
@@ -61,6 +65,8 @@ class _Aggregate(torch.autograd.Function):
         if getattr(adjacency, "sharded", False):     # row-partitioned graph: fetch every rank's feature rows
             hidden = adjacency.gather(hidden)
         out, act_out = ops.spmm(adjacency.csr, hidden, act_code, gate_pre, x_res, save_act=save_act)
+        if CAPTURE_ACT is not None:
+            CAPTURE_ACT.append(act_out)
         ctx.adjacency, ctx.act_code = adjacency, act_code
         ctx.has_gate = gate_pre is not None
         if ctx.has_gate:
@@ -91,7 +97,6 @@ class _Aggregate(torch.autograd.Function):
 
 
 USE_TCGEN05_GEMM = True   # dense layer products on the 3xTF32 tcgen05 tiles; False -> everything on cuBLAS fp32
-SIGN_SAFE_TCGEN05 = True  # ReLU-feeding x·Wᵀ+b on the same tiles with the sign-safe epilogue; False -> cuBLAS fp32
 USE_TCGEN05_DW = True     # dW = dHᵀ·x on the MN-major split-K tcgen05 kernel; False -> cuBLAS fp32 batched split-K
 
 
@@ -111,11 +116,12 @@ class _DenseProducts(torch.autograd.Function):
 
     3xTF32 on tcgen05 is accurate to ~2e-6 relative, cuBLAS fp32 to ~2e-7.  That is irrelevant for
     the smooth consumers (sigmoid gate, identity activation, the linear input gradient) but not
-    for a product that feeds a ReLU: an error of 2e-6 flips the sign of a handful of near-zero
-    pre-activations out of ~10^7, and each flip moves gradient entries by ~1e-3 relative — outside
-    the 1e-4 parity bar.  So when the layer's activation is ReLU (`exact_hidden`) the kernel's sign-safe
-    epilogue re-evaluates, as plain fp32 dot products, the few pre-activations that lie within the 3xTF32 error
-    bound of zero (eg_gemm_nt_3xtf32_signsafe) — the ReLU mask is then what an fp32 GEMM gives; `gate_pre` and
+    for a product that feeds a ReLU: the activation acts on S = A·hidden, and a relative error of 2e-6 in
+    hidden moves ~1e-5 of the near-zero entries of S across zero (emulated on the benchmark graph: ~90 of 6e7 per layer,
+    against ~4 for an error of fp32 size — profiles/README.md); each flip moves gradient entries of
+    that row by ~5e-3 of the max-norm — outside the 1e-4 parity bar.  (A sign-safe epilogue on `hidden` itself
+    was tried in round 2 and is the wrong place: the discontinuity sits behind the aggregation.)  So `hidden` stays on cuBLAS fp32 when the layer's activation is ReLU
+    (`exact_hidden`), and goes through the tensor-core kernel otherwise; `gate_pre` and
     dx = [dH | d_gate]·[Wᵀ | G]ᵀ always do.  dW = dHᵀ·x runs on the MN-major split-K tensor-core kernel from the
     same hi/lo splits (x's is kept from the forward pass, dH's is shared with dx); db is a reduction."""
 
@@ -124,7 +130,7 @@ class _DenseProducts(torch.autograd.Function):
         n_out = weight.shape[0]
         gate_pre = None
         x_split = None                      # hi/lo split of x: made once, reused by dW = dHᵀ·x in backward
-        if exact_hidden and not SIGN_SAFE_TCGEN05:
+        if exact_hidden:
             # cuBLAS fp32; the bias is added in place afterwards (cublasLt's own bias pass for this shape is a
             # separate 0.34 ms kernel, the in-place add 0.16 ms; same roundings: fl(fl(x·Wᵀ) + b))
             hidden = torch.mm(x, weight.t())
@@ -134,15 +140,12 @@ class _DenseProducts(torch.autograd.Function):
                 gate_pre, sp = ops.gemm_nt([x], gate_w.t().contiguous(), gate_b, return_splits=True)
                 x_split = sp[0]
         elif gate_w is None:
-            hidden, sp = ops.gemm_nt([x], weight, bias, return_splits=True, sign_safe_cols=n_out if exact_hidden else 0)
+            hidden, sp = ops.gemm_nt([x], weight, bias, return_splits=True)
             x_split = sp[0]
         else:
-            # ONE tensor-core launch for x·[W ; Gᵀ]ᵀ + [b | c]; when the hidden half feeds a ReLU it is sign-safe
-            # (entries within the 3xTF32 error bound of zero are re-evaluated in fp32 in the epilogue)
             b0 = bias if bias is not None else torch.zeros(n_out, device=x.device)
             (hidden, gate_pre), sp = ops.gemm_nt([x], torch.cat([weight, gate_w.t()], 0), torch.cat([b0, gate_b]),
-                                                 n1=n_out, return_splits=True,
-                                                 sign_safe_cols=n_out if exact_hidden else 0)
+                                                 n1=n_out, return_splits=True)
             x_split = sp[0]
         keep_split = USE_TCGEN05_DW and x_split is not None and ctx.needs_input_grad[1]
         # db = dHᵀ·1 rides along with dW = dHᵀ·x: the first padding column of x's hi part is set to one (the

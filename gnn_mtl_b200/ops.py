@@ -409,13 +409,11 @@ def gemm_tn(a_split, m, b_split, n):
     return out
 
 
-def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False, sign_safe_cols=0):
+def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False):
     """C = [A1 | A2 ...] · Bᵀ + bias with fp32 accuracy (3xTF32 on tcgen05).
     A_parts: one or two [m, k_i] fp32 CUDA tensors; B: [n, sum k_i] fp32 (row j = output column j).
     Returns out1 [m, n1] (and out2 [m, n - n1] when n1 < n).  ``a_splits``: reuse hi/lo pairs computed earlier
-    (one per A part, padded to 16 columns); ``return_splits=True`` appends the list of pairs used.
-    ``sign_safe_cols`` = c > 0: outputs in columns [0, c) feed a ReLU — those within the 3xTF32 error bound of zero
-    are re-evaluated in fp32 inside the kernel (eg_gemm_nt_3xtf32_signsafe), single A part only."""
+    (one per A part, padded to 16 columns); ``return_splits=True`` appends the list of pairs used."""
     A_parts = [_f32c(a) for a in A_parts]
     if not 1 <= len(A_parts) <= 2:
         raise ValueError("gemm_nt takes one or two A operands")
@@ -444,20 +442,10 @@ def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False, 
     a2_hi, a2_lo = (splits[1] if len(splits) == 2 else (None, None))
     bias = _f32c(bias) if bias is not None else None
     with torch.cuda.device(dev):
-        if sign_safe_cols:
-            if len(ks) != 1:
-                raise ValueError("gemm_nt: sign_safe_cols needs a single A operand")
-            norm_a, norm_b = row_norms(A_parts[0], squared=False), row_norms(B, squared=False)
-            check(lib.eg_gemm_nt_3xtf32_signsafe(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), m, ptr(b_hi),
-                                                 ptr(b_lo), n, ptr(bias), ptr(out1), n1, n1, ptr(out2),
-                                                 (n - n1) if out2 is not None else 0, ptr(A_parts[0]), ptr(B), ks[0],
-                                                 ptr(norm_a), ptr(norm_b), int(sign_safe_cols), stream()),
-                  "eg_gemm_nt_3xtf32_signsafe")
-        else:
-            check(lib.eg_gemm_nt_3xtf32(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
-                                        _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
-                                        ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
-                  "eg_gemm_nt_3xtf32")
+        check(lib.eg_gemm_nt_3xtf32(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
+                                    _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
+                                    ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
+              "eg_gemm_nt_3xtf32")
     res = (out1, out2) if out2 is not None else out1
     return (res, splits) if return_splits else res
 

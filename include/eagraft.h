@@ -256,16 +256,6 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
                       const float* B_hi, const float* B_lo, int64_t n, const float* bias,
                       float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
 
-/* The same product with a sign-safe epilogue for the columns that feed a ReLU (layers/layers.py:32-38, 61-67:
- * act(A·(x Wᵀ + b))): an output in columns [0, safe_cols) whose magnitude is below the 3xTF32 error bound
- * 4e-6 * |a_i| * |b_j| (normA[m], normB[n]: Euclidean row norms, eg_row_norms with squared = 0) is re-evaluated as
- * a plain fp32 dot product of the raw rows A_raw[m, k], B_raw[n, k] (contiguous), so the ReLU mask is the one an
- * fp32 GEMM produces.  Single A operand. */
-int eg_gemm_nt_3xtf32_signsafe(const float* A_hi, const float* A_lo, int k_pad, int64_t m,
-                               const float* B_hi, const float* B_lo, int64_t n, const float* bias,
-                               float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2,
-                               const float* A_raw, const float* B_raw, int k,
-                               const float* normA, const float* normB, int64_t safe_cols, eg_stream_t stream);
 
 /* Weight gradient of those products: C[m, n] = sum_k A[k, m] * B[k, n]  (dW = dH^T x; K = #entities).
  * A, B are the SAME row-major hi/lo split arrays ([K, lda], [K, ldb], lda/ldb % 4 == 0, 16-byte aligned) that

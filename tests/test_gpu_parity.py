@@ -121,31 +121,78 @@ def _oracle_stack(kg, x, params, acts):
     return xs, ps, y
 
 
+def _oracle_stack_pinned(kg, x, params, acts, gpu_act, tau=1e-5):
+    """The oracle's H-GCN stack (fp32, CPU — what the reference computes) with the ReLU branch PINNED to the GPU's
+    decision at the pre-activations the reference itself cannot decide: entries whose magnitude is below ``tau``
+    of the layer's mean |S|.  (fp32 CPU vs fp64 already disagree on a handful of those at the benchmark size —
+    which of them an implementation takes depends on its BLAS's summation order — and each such flip moves the
+    gradient of that row by ~5e-3 of the max-norm.)  Everywhere else the two masks must be IDENTICAL (asserted).
+    Returns (xs, ps, y, number of pinned entries, number of ReLU entries)."""
+    from oracle import ea_oracle as orc
+    tri = kg["triples"]
+    adj = orc.adjacency_torch_coo(kg["n"], tri[:, 0], tri[:, 2])
+    xs = x.clone().requires_grad_(True)
+    ps = [tuple(p.clone().requires_grad_(i < 2) for i, p in enumerate(q)) for q in params]
+    h, pinned, total = xs, 0, 0
+    for (W, b, G, c), act, ga in zip(ps, acts, gpu_act):
+        S = torch.sparse.mm(adj, F.linear(h, W, b))                  # layers/layers.py:61-64 (orc.gcn_layer)
+        if act == "relu":
+            own = S.detach() > 0
+            theirs = ga.cpu() > 0
+            differ = own != theirs
+            undecidable = S.detach().abs() < tau * S.detach().abs().mean()
+            assert not bool((differ & ~undecidable).any()), "ReLU branch differs at a decidable pre-activation"
+            pinned += int(differ.sum())
+            total += S.numel()
+            a = S * theirs.to(S.dtype)
+        else:
+            a = S
+        t = torch.sigmoid(h @ G + c)                                 # :69-76
+        h = t * a + (1.0 - t) * h
+    return xs, ps, h, pinned, total
+
+
 @pytest.mark.parametrize("shape,dim", [("tiny", 300), ("tiny", 128), ("tiny", 50), ("dbp15k", 300), ("dbp100k", 300)])
 def test_hgcn_stack_vs_oracle(shape, dim, dev):
     """2 encoder + 1 decoder highway layers (models/encoders.py:53-66, decoders.py:40-47); the last case is the
-    benchmark's own graph (200k nodes, BASELINE.json config 3): forward and every gradient against the oracle."""
+    benchmark's own graph (200k nodes, BASELINE.json config 3): forward and every gradient against the oracle.
+    At the two large sizes the ReLU branch of undecidable pre-activations is pinned (see _oracle_stack_pinned); the
+    forward comparison never needs it."""
     from gnn_mtl_b200.adjacency import DeviceAdjacency
-    from gnn_mtl_b200.layers.layers import HighWayGraphConvolution
+    from gnn_mtl_b200.layers import layers as L
     from gnn_mtl_b200.synth import make_kg_pair
     torch.manual_seed(1)
     kg = make_kg_pair(shape, dim=dim)
     x = torch.from_numpy(kg["x"])
     acts = [F.relu, F.relu, (lambda z: z)]
-    layers = [HighWayGraphConvolution(dim, dim, 0.0, a, True, -1, "cpu") for a in acts]
+    layers = [L.HighWayGraphConvolution(dim, dim, 0.0, a, True, -1, "cpu") for a in acts]
     params = [(l.linear.weight.detach(), l.linear.bias.detach(), l.kernel_gate, l.bias_gate) for l in layers]
-    xs, ps, y_ref = _oracle_stack(kg, x, params, ["relu", "relu", "identity"])
-    seed = torch.randn_like(y_ref)
-    (y_ref * seed).sum().backward()
+    seed = torch.randn(kg["n"], dim)
 
     adj = DeviceAdjacency.from_triples(kg["n"], kg["triples"], device=dev).to_torch_coo()
     xg = x.to(dev).requires_grad_(True)
     h = xg
-    for l in layers:
-        l.to(dev)
-        h, _ = l((h, adj))
+    L.CAPTURE_ACT = []
+    try:
+        for l in layers:
+            l.to(dev)
+            h, _ = l((h, adj))
+        gpu_act = L.CAPTURE_ACT
+    finally:
+        L.CAPTURE_ACT = None
     (h * seed.to(dev)).sum().backward()
-    assert relerr(h, y_ref) < REL
+
+    names = ["relu", "relu", "identity"]
+    xs0, ps0, y_plain = _oracle_stack(kg, x, params, names)
+    assert relerr(h, y_plain) < REL                                   # forward: the reference as it is
+    if shape == "tiny":
+        xs, ps, y_ref = xs0, ps0, y_plain
+    else:
+        xs, ps, y_ref, pinned, total = _oracle_stack_pinned(kg, x, params, names, gpu_act)
+        print("%s: %d of %d ReLU branches pinned" % (shape, pinned, total))
+        assert pinned <= max(4, total // 1000000)                      # a few per 10^7 (fp32 rounding), not more
+        assert relerr(h, y_ref) < REL
+    (y_ref * seed).sum().backward()
     assert relerr(xg.grad, xs.grad) < REL
     for l, p in zip(layers, ps):
         assert relerr(l.linear.weight.grad, p[0].grad) < REL
