@@ -48,6 +48,7 @@ SIGNATURES = {
     "eg_plan_dense": (C.c_int, [_i32, _vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "eg_sinkhorn_dense_workspace_bytes": (_sz, [_i32, _i64, _i64]),
     "eg_sinkhorn_sync_floor": (C.c_int, [_i64, _i64, _i32, _vp, _sz, _vp]),
+    "eg_issue_peak": (C.c_int, [_i32, _i32, C.POINTER(C.c_double), _vp, _vp]),
     "eg_sinkhorn_dense": (C.c_int, [_i32, _vp, _i64, _i64, _f64, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _sz,
                                     C.POINTER(C.c_int), C.POINTER(_f64), _vp]),
     "eg_row_norms": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),

@@ -45,11 +45,11 @@ int sinkhorn_tile2d_absorbs_read();
 // Returns EG_OK and sets *launched when the shape / device allow it; *launched = false -> caller uses another path.
 int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, double inv_reg, const float* a,
                            const float* b, float* log_u, float* log_v, const PersistState* warm, int start_iter,
-                           int max_iter, double stop_thr, float* part, size_t part_floats, PersistState* st,
+                           int max_iter, double stop_thr, void* part, size_t part_bytes, PersistState* st,
                            float absorb_log2, int force_fallback, cudaStream_t s, bool* launched);
 
 // Communication skeleton of one tile-kernel sweep (no mat-vec work), `iters` times: the latency floor of the design.
-int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* part, size_t part_floats,
+int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, void* part, size_t part_bytes,
                                       PersistState* st, cudaStream_t s, bool* launched);
 
 }  // namespace eg

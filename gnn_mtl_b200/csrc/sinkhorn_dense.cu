@@ -965,6 +965,7 @@ sinkhorn_onchip_scaling_kernel(const float* __restrict__ M, int64_t I, int J, in
     }
   // owned columns: warp 0, lane l < ncols
   float LV_own = 0.f, v_own = 1.0f, b_own = 0.f;
+  double LU_fold = 0.0, LV_fold = 0.0;                      // what the fold steps have moved into Kt since the hand-over
   if (warp == 0 && lane < ncols) { LV_own = log_v_in[col0 + lane] * kLog2e; b_own = b[col0 + lane]; }
   __syncthreads();
 
@@ -1187,8 +1188,10 @@ sinkhorn_onchip_scaling_kernel(const float* __restrict__ M, int64_t I, int J, in
         }
       }
       __syncthreads();
-      if (my_live) { LU_s[tid] += log2f(u_s[tid]); u_s[tid] = 1.0f; }
-      if (warp == 0 && lane < ncols) { LV_own += log2f(v_own); v_own = 1.0f; }
+      // folded amounts accumulate in fp64 (an fp32 potential of O(100) has an ulp of 1.5e-5: a fold per sweep would
+      // random-walk past the 1e-4 parity bar)
+      if (my_live) { LU_fold += (double)log2f(u_s[tid]); u_s[tid] = 1.0f; }
+      if (warp == 0 && lane < ncols) { LV_fold += (double)log2f(v_own); v_own = 1.0f; }
       u_big = false;
       if (cta == 0 && tid == 0) st->absorbs += 1;
       __syncthreads();
@@ -1201,8 +1204,9 @@ sinkhorn_onchip_scaling_kernel(const float* __restrict__ M, int64_t I, int J, in
   }
   __syncthreads();
   if (u_bad && tid == 0) st->fallback = 1;             // last sweep's row sums: no later phase R to publish it
-  if (my_live) log_u_out[row0 + my_row] = (LU_s[tid] + log2f(u_s[tid])) * kLn2;
-  if (warp == 0 && lane < ncols) log_v_out[col0 + lane] = (LV_own + log2f(v_own)) * kLn2;
+  if (my_live) log_u_out[row0 + my_row] = (float)(((double)LU_s[tid] + LU_fold + (double)log2f(u_s[tid])) * 0.69314718055994530942);
+  if (warp == 0 && lane < ncols)
+    log_v_out[col0 + lane] = (float)(((double)LV_own + LV_fold + (double)log2f(v_own)) * 0.69314718055994530942);
   if (cta == 0 && tid == 0) { st->sweeps = sweeps; st->final_buf = 0; st->err = err; }
 }
 
@@ -1331,7 +1335,7 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
           EG_CUDA(cudaMemsetAsync(w.state2, 0, sizeof(PersistState), s));
           bool launched = false;
           rc = sinkhorn_tile2d_launch(M, I, J, ld, 1.0 / reg, a, b, log_u, log_v, w.state, kWarmSweeps, max_iter,
-                                      stop_thr, w.part_m, (size_t)kNumSMs * (size_t)J, w.state2,
+                                      stop_thr, w.part_m, sizeof(float) * (size_t)kNumSMs * (size_t)J, w.state2,
                                       (float)g_tune_absorb_milli / 1000.0f, g_tune_force_fallback, s, &launched);
           if (rc) return rc;
           if (launched) {
@@ -1349,13 +1353,11 @@ static int sinkhorn_persistent_t(const T* M, int64_t I, int64_t J, double reg, c
               if (h_err) *h_err = fin.err;
               if (timing) {
                 const double n = std::max(1, hs[1].sweeps - kWarmSweeps);
-                fprintf(stderr, "[eagraft] tile2d sinkhorn: warm-up %d sweeps; %d sweeps, fallback %d, redo sweeps %d; CTA0 us/sweep: C %.2f | barrier %.2f | v %.2f | U dots %.2f | exchange+u %.2f\n",
+                fprintf(stderr, "[eagraft] tile2d sinkhorn: warm-up %d sweeps; %d sweeps, fallback %d, redo sweeps %d; CTA0 us/sweep: C %.2f | column exchange %.2f | v %.2f | U dots %.2f | row exchange + u %.2f\n",
                         hs[0].sweeps, hs[1].sweeps, hs[1].fallback, hs[2].sweeps, hs[1].t_phase[0] / 1e3 / n,
                         hs[1].t_phase[1] / 1e3 / n, hs[1].t_phase[2] / 1e3 / n, hs[1].t_phase[3] / 1e3 / n,
                         hs[1].t_phase[4] / 1e3 / n);
-                if (hs[1].fallback >= 2)
-                  fprintf(stderr, "[eagraft] tile2d barrier timeout: CTA %llu saw %llu arrivals, waited for %llu\n",
-                          hs[1].t_phase[6] >> 32, hs[1].t_phase[6] & 0xffffffffull, hs[1].t_phase[7]);
+                if (hs[1].fallback >= 2) fprintf(stderr, "[eagraft] tile2d: a wait on another CTA timed out\n");
               }
             } else {
               // every sweep runs and nothing is read back: the whole solve stays asynchronous
@@ -1573,7 +1575,7 @@ int eg_sinkhorn_sync_floor(int64_t n_rows, int64_t n_cols, int iters, void* ws, 
   SolveWs<float> w = carve_solve<float>(ws, n_rows, n_cols);
   if (ws_bytes < w.total) return EG_ERR_WORKSPACE;
   bool launched = false;
-  int rc = sinkhorn_tile2d_sync_floor_launch(n_rows, n_cols, iters, w.part_m, (size_t)kNumSMs * (size_t)n_cols, w.state2,
+  int rc = sinkhorn_tile2d_sync_floor_launch(n_rows, n_cols, iters, w.part_m, sizeof(float) * (size_t)kNumSMs * (size_t)n_cols, w.state2,
                                              as_stream(stream_), &launched);
   if (rc) return rc;
   return launched ? EG_OK : EG_ERR_UNSUPPORTED;

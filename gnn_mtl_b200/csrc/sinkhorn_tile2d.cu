@@ -35,6 +35,10 @@ constexpr int kT2QG = 3;            // float4 column groups per lane -> at most 
 constexpr int kT2RRW = 6;           // rows per warp kept in registers
 constexpr int kT2MaxRowsPerWarp = 16;
 constexpr int kT2MaxClusters = 32;
+constexpr int kT2RedStride = kT2QG * 32 * 4;                         // floats per warp in the column-partial staging
+constexpr int kT2RowStride = kT2Warps * kT2MaxRowsPerWarp + kT2MaxRowsPerWarp;   // floats per peer in the row-partial inbox
+// (compile-time strides: the 16 + 8 addresses of the two fixed-order reductions become immediates, not registers)
+constexpr long long kT2WaitClocks = 40000000ll;     // ~20 ms of SM clocks: bound of every wait on another CTA
 
 __device__ int g_dev_tile2d_absorbs = 0;
 
@@ -44,7 +48,7 @@ struct T2Params {
   float* log_u; float* log_v;               // in: warm-up potentials (natural log); out: accepted potentials
   const PersistState* warm;                 // state of the warm-up launch (nullable)
   int start_iter, max_iter; double stop_thr;
-  float* part;                              // [2][kT2CS][nc][gs * 4] column partials
+  uint32_t* part;                           // [2][kT2CS][nc][t2_words(gs)] sign-tagged words (zeroed before the launch)
   PersistState* st;
   int nc;                                   // clusters = row blocks
   int rows_per_cluster;                     // <= 16 * nrw
@@ -52,10 +56,17 @@ struct T2Params {
   int gs;                                   // float4 groups per column slice (<= 96)
   float absorb_log2; int force_fallback;
 };
+// words one CTA publishes per sweep: its column partials + one control word (total marginal error of the last check)
+__host__ __device__ inline int t2_words(int gs) { return gs * 4 + 4; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ uint32_t cluster_idx() {
@@ -75,51 +86,48 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_relaxed_f32(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
+// Every exchanged number is a sum of non-negative terms, so its sign bit is free to carry the hand-shake: the word of
+// sweep s lives in slot (s & 1) and is published with sign bit t2_phase(s); the previous occupant of the slot (sweep
+// s - 2, or the zero fill before the launch) carries the opposite bit, and the occupant of sweep s + 2 cannot appear
+// before every reader of sweep s has published its own sweep s + 1.  A reader therefore polls the data itself: no
+// barrier, no fence, no second round trip, 4 bytes per number.  (Relaxed gpu-scope accesses are served at the L2.)
+__device__ __forceinline__ uint32_t t2_phase(int sweep_from_start) { return (((uint32_t)sweep_from_start >> 1) & 1u) ^ 1u; }
+__device__ __forceinline__ void st_signed(uint32_t* p, uint32_t phase, float v) {
+  const uint32_t w = (__float_as_uint(v) & 0x7fffffffu) | (phase << 31);
+  asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
 }
-__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// predicated load (no branch around it: the 16 polls of a round issue back to back)
+__device__ __forceinline__ void ld_signed_if(uint32_t& w, const char* p, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %2, 0;\n\t@pp ld.relaxed.gpu.global.b32 %0, [%1];\n\t}"
+               : "+r"(w) : "l"(p), "r"(pred) : "memory");
 }
-__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Grid barrier on a monotonically increasing counter (all CTAs co-resident: verified once per device by
-// t2_probe_kernel, and the launch is cooperative).  The wait is bounded: after 20 ms without progress (a sweep
-// takes microseconds) the CTA raises the sticky `fallback = 2`, every waiter sees it and leaves its sweep loop at
-// the next check — the solve is then redone by the log-domain kernel instead of hanging the device.
-__device__ __forceinline__ void t2_grid_barrier(PersistState* st, unsigned int& target, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += nblocks;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->barrier) : "memory");
-    unsigned int seen;
-    unsigned int spins = 0;
-    const long long t0 = clock64();
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->barrier) : "memory");
-      if ((int)(seen - target) >= 0) break;
-      if ((++spins & 63u) == 0) {
-        if (ld_relaxed_s32(&st->fallback) >= 2) break;   // aborted solve: nobody waits any more
-        if (clock64() - t0 > 40000000ll) {               // ~20 ms of SM clocks
-          if (atomicMax(&st->fallback, 2) < 2) {         // first to give up: leave a trace for EG_PERSIST_TIMING
-            st->t_phase[6] = ((unsigned long long)blockIdx.x << 32) | seen;
-            st->t_phase[7] = target;
-          }
-          atomicMax(&st->flag_code, 0x7fffffff);       // "raised before every sweep": acted on at once
-          break;
-        }
-      }
-    }
+// Polls up to 16 words `stride_bytes` apart until each carries `phase`; returns their sum in index order (fixed order
+// -> every CTA that adds the same words gets the same bits).  Gives up (sum of what arrived) when `*give_up` is set or
+// after kT2WaitClocks, and reports that through *timed_out.
+__device__ __forceinline__ float t2_poll_sum(const uint32_t* src, uint32_t stride_bytes, int n, uint32_t phase,
+                                             volatile int* give_up, bool* timed_out) {
+  uint32_t w[16];
+  uint32_t pend = (n >= 16) ? 0xffffu : ((1u << n) - 1u);
+  const uint32_t want = phase << 31;
+  const char* p0 = reinterpret_cast<const char*>(src);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = want ^ 0x80000000u;
+  long long t0 = 0;
+  while (true) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ld_signed_if(w[k], p0 + (size_t)((uint32_t)k * stride_bytes), (pend >> k) & 1u);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (((w[k] ^ want) >> 31) == 0u) pend &= ~(1u << k);
+    if (pend == 0) break;
+    if (t0 == 0) t0 = clock64();
+    if (*give_up != 0 || clock64() - t0 > kT2WaitClocks) { *timed_out = true; break; }
   }
-  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < n && !((pend >> k) & 1u)) s += __uint_as_float(w[k] & 0x7fffffffu);
+  return s;
 }
 
 // 16 values per lane -> every lane ends with the warp-wide sum of value (lane & 15): 15 + 1 shuffles.
@@ -139,18 +147,28 @@ __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) 
   return t;
 }
 
-__device__ __forceinline__ float dot4(const float4& k, const float4& v) {
-  return (k.x * v.x + k.y * v.y) + (k.z * v.z + k.w * v.w);
+// Packed fp32 FMA (FFMA2): two lanes of a float2 per issue slot; with b = (u, u) ptxas uses the scalar-broadcast form.
+__device__ __forceinline__ void fma2(float2& acc, const float2 a, const float2 b) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
 }
-__device__ __forceinline__ void fma4(float4& acc, const float4& k, float u) {
-  acc.x = fmaf(k.x, u, acc.x); acc.y = fmaf(k.y, u, acc.y); acc.z = fmaf(k.z, u, acc.z); acc.w = fmaf(k.w, u, acc.w);
+struct Acc4 { float2 lo, hi; };     // one float4 accumulator as two packed halves
+__device__ __forceinline__ void fma4s(Acc4& acc, const float4& k, float u) {      // acc += k * u
+  const float2 uu = make_float2(u, u);
+  fma2(acc.lo, make_float2(k.x, k.y), uu);
+  fma2(acc.hi, make_float2(k.z, k.w), uu);
+}
+__device__ __forceinline__ void fma4v(float2& acc, const float4& k, const float4& v) {   // acc += (k.xy*v.xy) + (k.zw*v.zw)
+  fma2(acc, make_float2(k.x, k.y), make_float2(v.x, v.y));
+  fma2(acc, make_float2(k.z, k.w), make_float2(v.z, v.w));
 }
 __device__ __forceinline__ void scale4(float4& k, float u, const float4& v) {
   k.x *= u * v.x; k.y *= u * v.y; k.z *= u * v.z; k.w *= u * v.w;
 }
 
 struct T2Smem {            // offsets in floats into dynamic shared memory
-  int u, LU, a, v, LV, b, red_c, rowpart, flags, bak_f, bak_g, kt;
+  int LU, LV, bak_f, bak_g, u, a, v, b, red_c, rowpart, ctrl_in, flags, red_e, kt;
   size_t bytes;
 };
 __host__ __device__ inline T2Smem t2_carve(int nrw, int gs) {
@@ -159,30 +177,35 @@ __host__ __device__ inline T2Smem t2_carve(int nrw, int gs) {
   const int nc4 = gs * 4;
   int off = 0;
   auto take = [&](int n) { int o = off; off += (n + 3) / 4 * 4; return o; };
-  s.u = take(rb); s.LU = take(rb); s.a = take(rb);
-  s.v = take(nc4); s.LV = take(nc4); s.b = take(nc4);
-  s.red_c = take(kT2Warps * nc4);
-  s.rowpart = take(2 * kT2CS * rb);
+  s.LU = take(2 * rb); s.LV = take(2 * nc4);           // doubles: folded potentials keep their low bits
+  s.bak_f = take(2 * rb); s.bak_g = take(2 * nc4);     // doubles
+  s.red_e = take(2 * kT2Warps);                        // doubles
+  s.u = take(rb); s.a = take(rb);
+  s.v = take(nc4); s.b = take(nc4);
+  s.red_c = take(kT2Warps * kT2RedStride);
+  s.rowpart = take(2 * kT2CS * kT2RowStride);
+  s.ctrl_in = take(2 * kT2CS);                         // [2][kT2CS] marginal-error partials pushed by the cluster peers
   s.flags = take(8);
-  s.bak_f = take(2 * rb);       // doubles
-  s.bak_g = take(2 * nc4);      // doubles
   s.kt = take(0);
   const int srw = nrw > kT2RRW ? nrw - kT2RRW : 0;
   s.bytes = sizeof(float) * (size_t)off + sizeof(float4) * (size_t)kT2Warps * srw * gs;
   return s;
 }
 
-__global__ void __launch_bounds__(kT2Threads, 1)
+__global__ void __cluster_dims__(kT2CS, 1, 1) __launch_bounds__(kT2Threads, 1)
 sinkhorn_tile2d_kernel(const T2Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw_t2[];
   float* sm = reinterpret_cast<float*>(smem_raw_t2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = (int)cluster_ctarank(), p = (int)cluster_idx();
   const int NC = P.nc;
-  const unsigned int nb = (unsigned int)(NC * kT2CS);
   PersistState* st = P.st;
   // the warm-up launch already met the stop rule: its potentials are the answer
   if (P.warm != nullptr && P.warm->sweeps < P.start_iter) return;
+  if (cluster_nctarank() != (uint32_t)kT2CS) {          // launched without its cluster shape: the host redoes the solve
+    if (tid == 0) atomicMax(&st->fallback, 2);
+    return;
+  }
 
   const int nrw = P.nrw, SRW = nrw > kT2RRW ? nrw - kT2RRW : 0;
   const int Rb = P.rows_per_cluster;
@@ -190,16 +213,18 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   const int R = (int)max((int64_t)0, min((int64_t)Rb, P.I - row_base));       // live rows of this cluster
   const int ng = P.J / 4, Gs = P.gs, g_base = q * Gs;
   const int Gq = max(0, min(Gs, ng - g_base));                                  // live column groups of this slice
-  const int nc4 = Gs * 4, ncols = Gq * 4;
+  const int nc4 = Gs * 4, ncols = Gq * 4, W = t2_words(Gs);
   const int rb_pad = kT2Warps * nrw + kT2MaxRowsPerWarp;
   const T2Smem L = t2_carve(nrw, Gs);
-  float* u_s = sm + L.u; float* LU_s = sm + L.LU; float* a_s = sm + L.a;
-  float* v_s = sm + L.v; float* LV_s = sm + L.LV; float* b_s = sm + L.b;
+  double* LU_s = reinterpret_cast<double*>(sm + L.LU); double* LV_s = reinterpret_cast<double*>(sm + L.LV);
+  double* bak_f = reinterpret_cast<double*>(sm + L.bak_f); double* bak_g = reinterpret_cast<double*>(sm + L.bak_g);
+  double* red_e = reinterpret_cast<double*>(sm + L.red_e);
+  float* u_s = sm + L.u; float* a_s = sm + L.a; float* v_s = sm + L.v; float* b_s = sm + L.b;
   float* red_c = sm + L.red_c;
-  float* rowpart = sm + L.rowpart;                       // [2][kT2CS][rb_pad]
-  int* flag_s = reinterpret_cast<int*>(sm + L.flags);    // [0] fold v, [1] fold u, [2] bad sum, [3] break code
-  double* bak_f = reinterpret_cast<double*>(sm + L.bak_f);
-  double* bak_g = reinterpret_cast<double*>(sm + L.bak_g);
+  float* rowpart = sm + L.rowpart;                       // [2][kT2CS][kT2RowStride]
+  float* ctrl_in = sm + L.ctrl_in;                       // [2][kT2CS]
+  int* flag_s = reinterpret_cast<int*>(sm + L.flags);    // [0] fold v, [1] fold u, [2] bad sum, [3] break code, [4] gave up waiting
+  float* ctrl_f = reinterpret_cast<float*>(flag_s + 5);  // [5] total error of the last check (to publish), [6] incoming total
   float4* kt_s = reinterpret_cast<float4*>(sm + L.kt);   // [warp][SRW][Gs]
   const float kAbsorb = P.absorb_log2;
 
@@ -207,13 +232,13 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   for (int r = tid; r < rb_pad; r += kT2Threads) {
     const bool live = r < R;
     u_s[r] = 1.0f;
-    LU_s[r] = live ? P.log_u[row_base + r] * kLog2e : 0.f;
+    LU_s[r] = live ? (double)P.log_u[row_base + r] * 1.4426950408889634074 : 0.0;
     a_s[r] = live ? P.a[row_base + r] : 0.f;
   }
   for (int c = tid; c < nc4; c += kT2Threads) {
     const bool live = c < ncols;
     v_s[c] = live ? 1.0f : 0.f;
-    LV_s[c] = live ? P.log_v[(int64_t)g_base * 4 + c] * kLog2e : 0.f;
+    LV_s[c] = live ? (double)P.log_v[(int64_t)g_base * 4 + c] * 1.4426950408889634074 : 0.0;
     b_s[c] = live ? P.b[(int64_t)g_base * 4 + c] : 0.f;
   }
   if (tid < 8) flag_s[tid] = 0;
@@ -232,13 +257,13 @@ sinkhorn_tile2d_kernel(const T2Params P) {
     float4 k = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lr < R && gok[g]) {
       const float4 m = *reinterpret_cast<const float4*>(P.M + (row_base + lr) * P.ld + 4 * (int64_t)(g_base + lg[g]));
-      const float4 lv = reinterpret_cast<const float4*>(LV_s)[lg[g]];
-      const double lu = (double)LU_s[lr], i2 = P.inv2;
+      const double lu = LU_s[lr], i2 = P.inv2;
+      const double* lv = LV_s + 4 * lg[g];
       // exponent in fp64 (|M/reg| reaches hundreds: an fp32 fma would leave ~1e-5 relative in the entry), then ex2
-      k.x = ex2f((float)(lu + (double)lv.x - (double)m.x * i2));
-      k.y = ex2f((float)(lu + (double)lv.y - (double)m.y * i2));
-      k.z = ex2f((float)(lu + (double)lv.z - (double)m.z * i2));
-      k.w = ex2f((float)(lu + (double)lv.w - (double)m.w * i2));
+      k.x = ex2f((float)(lu + lv[0] - (double)m.x * i2));
+      k.y = ex2f((float)(lu + lv[1] - (double)m.y * i2));
+      k.z = ex2f((float)(lu + lv[2] - (double)m.z * i2));
+      k.w = ex2f((float)(lu + lv[3] - (double)m.w * i2));
     }
     return k;
   };
@@ -253,77 +278,89 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       if (lg[g] < Gs) kt_s[(warp * SRW + sr) * Gs + lg[g]] = build(wrow0 + kT2RRW + sr, g);
   __syncthreads();
 
-  unsigned int target = 0;
   int cpt = P.start_iter, sweeps = P.start_iter;
   double err = 1.0;
   bool stop_hit = false;
-  int pending_slot = -1, pending_cpt = 0;      // a marginal-error check whose sum is complete after the next barrier
+  int pending_cpt = -1;                          // sweep whose marginal-error check is decided one exchange later
   const bool timer = (blockIdx.x == 0 && tid == 0);
   const uint32_t rowpart_saddr = (uint32_t)__cvta_generic_to_shared(rowpart);
+  const uint32_t ctrl_saddr = (uint32_t)__cvta_generic_to_shared(ctrl_in);
+
+  // Column exchange of one sweep: publish my partials (sign-tagged), then wait for every cluster's partials of MY
+  // columns.  Returns the cluster-order sum for thread `tid` (< nc4); thread nc4 fetches the control word of cluster 0.
+  auto exchange = [&](int sweep, float mine, bool publish_partials) -> float {
+    const uint32_t phase = t2_phase(sweep - P.start_iter);
+    uint32_t* base = P.part + ((size_t)((sweep & 1) * kT2CS + q) * NC) * W;
+    if (tid < nc4) { if (publish_partials) st_signed(base + (size_t)p * W + tid, phase, mine); }
+    else if (tid == nc4) st_signed(base + (size_t)p * W + nc4, phase, ctrl_f[0]);
+    float s = 0.f;
+    if ((publish_partials && tid < nc4) || tid == nc4) {
+      const int n_src = (tid == nc4) ? 1 : NC;             // the control word comes from cluster 0 only
+      bool timed_out = false;
+      for (int pp = 0; pp < n_src; pp += 16)
+        s += t2_poll_sum(base + (size_t)pp * W + tid, 4u * (uint32_t)W, min(16, n_src - pp), phase,
+                         reinterpret_cast<volatile int*>(flag_s) + 4, &timed_out);
+      if (timed_out && reinterpret_cast<volatile int*>(flag_s)[4] == 0) {      // never hang: the host redoes the solve
+        reinterpret_cast<volatile int*>(flag_s)[4] = 1;
+        atomicMax(&st->fallback, 2);
+      }
+    }
+    return s;
+  };
 
   for (cpt = P.start_iter; cpt < P.max_iter; ++cpt) {
     const int par = cpt & 1;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     if (timer) t0 = gtime();
-    // ---- C: column partials of my tile (thread: 3 column groups x the warp's rows) ---------------------------
+    // ---- C: column partials of my tile (thread: 3 column groups x the warp's rows), packed FMAs ----------------
     {
-      float4 acc[kT2QG];
+      Acc4 acc[kT2QG];
 #pragma unroll
-      for (int g = 0; g < kT2QG; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < kT2QG; ++g) { acc[g].lo = make_float2(0.f, 0.f); acc[g].hi = make_float2(0.f, 0.f); }
+      float ur[kT2RRW];
 #pragma unroll
-      for (int r = 0; r < kT2RRW; ++r) {
-        const float ur = u_s[wrow0 + r];
+      for (int r = 0; r < kT2RRW; ++r) ur[r] = u_s[wrow0 + r];
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g) fma4(acc[g], kreg[r][g], ur);
-      }
+      for (int r = 0; r < kT2RRW; ++r)
+#pragma unroll
+        for (int g = 0; g < kT2QG; ++g) fma4s(acc[g], kreg[r][g], ur[r]);
       const float4* kw = kt_s + warp * SRW * Gs;
 #pragma unroll 2
       for (int sr = 0; sr < SRW; ++sr) {
-        const float ur = u_s[wrow0 + kT2RRW + sr];
+        const float us = u_s[wrow0 + kT2RRW + sr];
         float4 k[kT2QG];
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g) k[g] = kw[sr * Gs + lgc[g]];
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g) fma4(acc[g], k[g], ur);
+        for (int g = 0; g < kT2QG; ++g) fma4s(acc[g], k[g], us);
       }
 #pragma unroll
       for (int g = 0; g < kT2QG; ++g)
-        if (lg[g] < Gs) reinterpret_cast<float4*>(red_c)[warp * Gs + lg[g]] = gok[g] ? acc[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lg[g] < Gs)
+          reinterpret_cast<float4*>(red_c)[warp * (kT2RedStride / 4) + lg[g]] =
+              gok[g] ? make_float4(acc[g].lo.x, acc[g].lo.y, acc[g].hi.x, acc[g].hi.y) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    float* my_part = P.part + ((size_t)(par * kT2CS + q) * NC) * nc4;
+    float mine = 0.f;
     if (tid < nc4) {
-      float s = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < kT2Warps; ++w2) s += red_c[w2 * nc4 + tid];
-      my_part[(size_t)p * nc4 + tid] = s;
+      for (int w2 = 0; w2 < kT2Warps; ++w2) mine += red_c[w2 * kT2RedStride + tid];
     }
     if (timer) t1 = gtime();
-    t2_grid_barrier(st, target, nb);
-    if (timer) t2 = gtime();
     // ---- all clusters' partials of MY columns -> v on my slice (every CTA of slice q computes the same bits) ----
+    const float s = exchange(cpt, mine, true);
+    if (timer) t2 = gtime();
     const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
-    const int slot = check ? ((cpt - 1) / 10) & 127 : 0;
     if (check) {   // back-up of the iterate the check refers to (before sweep cpt touches it), as full potentials
-      for (int r = tid; r < rb_pad; r += kT2Threads) bak_f[r] = (double)LU_s[r] + log2((double)u_s[r]);
+      for (int r = tid; r < rb_pad; r += kT2Threads) bak_f[r] = LU_s[r] + log2((double)u_s[r]);
     }
     {
-      float s = 0.f;
       double d2 = 0.0;
       if (tid < nc4) {
-        // all partials requested before the first add (one L2 round trip, not NC of them); summed in cluster order
-        const float* src = my_part + tid;
-        for (int pp = 0; pp < NC; pp += 16) {
-          float t[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) t[k] = (pp + k < NC) ? ld_relaxed_f32(src + (size_t)(pp + k) * nc4) : 0.f;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) s += t[k];
-        }
         const bool live = tid < ncols;
         const float v_old = v_s[tid];
         if (check) {
-          bak_g[tid] = live ? (double)LV_s[tid] + log2((double)v_old) : 0.0;
+          bak_g[tid] = live ? LV_s[tid] + log2((double)v_old) : 0.0;
           if (live && p == 0) {
             const double d = (double)(v_old * s) - (double)b_s[tid];
             d2 = d * d;
@@ -335,40 +372,25 @@ sinkhorn_tile2d_kernel(const T2Params P) {
           if (fabsf(lg2f(vn)) > kAbsorb) flag_s[0] = 1;
           v_s[tid] = vn;
         }
+      } else if (tid == nc4) {
+        ctrl_f[1] = s;                           // total marginal error of the previous sweep's check (from cluster 0)
       }
-      if (check && p == 0) {                 // CTA-uniform: every lane of every warp takes part (d2 = 0 past nc4)
+      if (check && p == 0) {                     // CTA-uniform: every lane takes part; fixed order -> deterministic
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        if (lane == 0 && d2 != 0.0) atomicAdd(&st->err2[slot], d2);
-      }
-      // flags raised during an EARLIER sweep are complete and identical for every CTA after this sweep's barrier
-      if (tid == 0) {
-        const int code = ld_relaxed_s32(&st->flag_code);
-        int brk = 0;
-        if (code != 0 && (0x7fffffff - code) < cpt) brk = 1;
-        if (brk == 0 && pending_slot >= 0) {
-          const double e2 = ld_relaxed_f64(&st->err2[pending_slot]);
-          if (!(sqrt(e2) > P.stop_thr)) brk = 2;
-        }
-        flag_s[3] = brk;
+        if (lane == 0) red_e[warp] = d2;
       }
     }
     __syncthreads();
     if (timer) t3 = gtime();
-    {
-      const int brk = flag_s[3];
-      if (pending_slot >= 0) {
-        err = sqrt(ld_relaxed_f64(&st->err2[pending_slot]));     // complete: same value in every thread
-        pending_slot = -1;
-      }
-      if (brk == 1) break;
-      if (brk == 2) { stop_hit = true; break; }
-      if (flag_s[2] && tid == 0) {
-        atomicMax(&st->fallback, 1);
-        atomicMax(&st->flag_code, 0x7fffffff - cpt);
-      }
-      if (check) { pending_slot = slot; pending_cpt = cpt; }
+    if (pending_cpt >= 0) {                      // the check issued one sweep ago: same word in every CTA
+      err = sqrt((double)ctrl_f[1]);
+      const bool stop = !(err > P.stop_thr);
+      if (stop) { stop_hit = true; break; }
+      pending_cpt = -1;
     }
+    if (flag_s[2] && tid == 0) atomicMax(&st->fallback, 1);
+    if (check) pending_cpt = cpt;
     float4 vq[kT2QG];
 #pragma unroll
     for (int g = 0; g < kT2QG; ++g) vq[g] = gok[g] ? reinterpret_cast<const float4*>(v_s)[lg[g]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -383,7 +405,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g)
           if (gok[g]) scale4(kt_s[(warp * SRW + sr) * Gs + lg[g]], 1.0f, vq[g]);
-      if (tid < ncols) { LV_s[tid] += log2f(v_s[tid]); v_s[tid] = 1.0f; }
+      if (tid < ncols) { LV_s[tid] += log2((double)v_s[tid]); v_s[tid] = 1.0f; }
       if (tid == 0) { flag_s[0] = 0; if (blockIdx.x == 0) atomicAdd(&g_dev_tile2d_absorbs, 1); }
 #pragma unroll
       for (int g = 0; g < kT2QG; ++g) if (gok[g]) vq[g] = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -395,8 +417,12 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) dots[r] = 0.f;
 #pragma unroll
-      for (int r = 0; r < kT2RRW; ++r)
-        dots[r] = (dot4(kreg[r][0], vq[0]) + dot4(kreg[r][1], vq[1])) + dot4(kreg[r][2], vq[2]);
+      for (int r = 0; r < kT2RRW; ++r) {
+        float2 d2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < kT2QG; ++g) fma4v(d2, kreg[r][g], vq[g]);
+        dots[r] = d2.x + d2.y;
+      }
       const float4* kw = kt_s + warp * SRW * Gs;
 #pragma unroll
       for (int sr = 0; sr < kT2MaxRowsPerWarp - kT2RRW; ++sr) {
@@ -404,49 +430,65 @@ sinkhorn_tile2d_kernel(const T2Params P) {
           float4 k[kT2QG];
 #pragma unroll
           for (int g = 0; g < kT2QG; ++g) k[g] = kw[sr * Gs + lgc[g]];
-          dots[kT2RRW + sr] = (dot4(k[0], vq[0]) + dot4(k[1], vq[1])) + dot4(k[2], vq[2]);
+          float2 d2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int g = 0; g < kT2QG; ++g) fma4v(d2, k[g], vq[g]);
+          dots[kT2RRW + sr] = d2.x + d2.y;
         }
       }
       const float tot = warp_transpose_sum16(dots, lane);
       if (timer) t4 = gtime();
       const int r = lane & 15;
       if (r < nrw) {
-        const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * rb_pad + wrow0 + r);
+        const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * kT2RowStride + wrow0 + r);
         const int q0 = (lane >> 4) * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) st_cluster_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot);
       }
+      if (check && tid < kT2CS) {               // my share of the marginal error rides along (zero outside cluster 0)
+        double e = 0.0;
+        if (p == 0) {
+#pragma unroll
+          for (int w2 = 0; w2 < kT2Warps; ++w2) e += red_e[w2];
+        }
+        st_cluster_f32(mapa_shared(ctrl_saddr + 4u * (uint32_t)(par * kT2CS + q), (uint32_t)tid), (float)e);
+      }
     }
     cluster_sync_all();
     if (tid < rb_pad) {
-      const float* rp = rowpart + (par * kT2CS) * rb_pad + tid;
-      float s = 0.f;
+      const float* rp = rowpart + (par * kT2CS) * kT2RowStride + tid;
+      float rs = 0.f;
 #pragma unroll
-      for (int k = 0; k < kT2CS; ++k) s += rp[k * rb_pad];
+      for (int k = 0; k < kT2CS; ++k) rs += rp[k * kT2RowStride];
       if (tid < R) {
-        const float un = a_s[tid] / s;
-        if (!(s > 0.f) || !(un < CUDART_INF_F) || !(un > 0.f)) flag_s[2] = 1;
+        const float un = a_s[tid] / rs;
+        if (!(rs > 0.f) || !(un < CUDART_INF_F) || !(un > 0.f)) flag_s[2] = 1;
         if (fabsf(lg2f(un)) > kAbsorb) flag_s[1] = 1;
         u_s[tid] = un;
       }
+    } else if (check && tid == kT2Threads - 1) {
+      float e = 0.f;
+#pragma unroll
+      for (int k = 0; k < kT2CS; ++k) e += ctrl_in[par * kT2CS + k];
+      ctrl_f[0] = e;                             // cluster 0: the whole squared error, published with the next sweep
     }
     __syncthreads();
     if (flag_s[1]) {
       // fold u into the tile and the row potentials (every CTA of this cluster takes the same decision)
 #pragma unroll
       for (int r = 0; r < kT2RRW; ++r) {
-        const float ur = u_s[wrow0 + r];
+        const float us = u_s[wrow0 + r];
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g) { kreg[r][g].x *= ur; kreg[r][g].y *= ur; kreg[r][g].z *= ur; kreg[r][g].w *= ur; }
+        for (int g = 0; g < kT2QG; ++g) { kreg[r][g].x *= us; kreg[r][g].y *= us; kreg[r][g].z *= us; kreg[r][g].w *= us; }
       }
       for (int sr = 0; sr < SRW; ++sr) {
-        const float ur = u_s[wrow0 + kT2RRW + sr];
+        const float us = u_s[wrow0 + kT2RRW + sr];
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g)
-          if (gok[g]) { float4& k = kt_s[(warp * SRW + sr) * Gs + lg[g]]; k.x *= ur; k.y *= ur; k.z *= ur; k.w *= ur; }
+          if (gok[g]) { float4& k = kt_s[(warp * SRW + sr) * Gs + lg[g]]; k.x *= us; k.y *= us; k.z *= us; k.w *= us; }
       }
       __syncthreads();
-      if (tid < R) { LU_s[tid] += log2f(u_s[tid]); u_s[tid] = 1.0f; }
+      if (tid < R) { LU_s[tid] += log2((double)u_s[tid]); u_s[tid] = 1.0f; }
       if (tid == 0) flag_s[1] = 0;
       __syncthreads();
     }
@@ -457,27 +499,27 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       st->t_phase[3] += t4 - t3; st->t_phase[4] += t5 - t4;
     }
   }
-  // a check issued in the very last sweep: its sum is complete one barrier later
-  if (cpt >= P.max_iter && pending_slot >= 0) {
-    if (flag_s[2] && tid == 0) { atomicMax(&st->fallback, 1); }
-    t2_grid_barrier(st, target, nb);
-    err = sqrt(ld_relaxed_f64(&st->err2[pending_slot]));
+  // a check issued in the very last sweep: its total travels with one more (control-only) exchange
+  if (cpt >= P.max_iter && pending_cpt >= 0) {
+    const float e = exchange(P.max_iter, 0.f, false);
+    if (tid == nc4) ctrl_f[1] = e;
+    __syncthreads();
+    err = sqrt((double)ctrl_f[1]);
     if (!(err > P.stop_thr)) stop_hit = true;
-  } else if (cpt >= P.max_iter) {
-    if (flag_s[2] && tid == 0) atomicMax(&st->fallback, 1);     // last sweep's sums: no later barrier publishes them
   }
+  if (flag_s[2] && tid == 0) atomicMax(&st->fallback, 1);
   __syncthreads();
   // ---- outputs (natural-log potentials, composed in fp64) ------------------------------------------------------
   const double ln2 = 0.69314718055994530942;
   if (q == 0) {
     for (int r = tid; r < R; r += kT2Threads) {
-      const double f = stop_hit ? bak_f[r] : (double)LU_s[r] + log2((double)u_s[r]);
+      const double f = stop_hit ? bak_f[r] : LU_s[r] + log2((double)u_s[r]);
       P.log_u[row_base + r] = (float)(f * ln2);
     }
   }
   if (p == 0) {
     for (int c = tid; c < ncols; c += kT2Threads) {
-      const double g = stop_hit ? bak_g[c] : (double)LV_s[c] + log2((double)v_s[c]);
+      const double g = stop_hit ? bak_g[c] : LV_s[c] + log2((double)v_s[c]);
       P.log_v[(int64_t)g_base * 4 + c] = (float)(g * ln2);
     }
   }
@@ -489,61 +531,55 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   }
 }
 
-// The communication skeleton of one sweep with no mat-vec work: column partials through global memory + the grid
-// barrier + NC partial reads, then the row-partial push through distributed shared memory + the cluster barrier.
-// bench.py times it to state the latency floor of this design next to the measured sweep time.
-__global__ void __launch_bounds__(kT2Threads, 1)
-sinkhorn_tile2d_sync_floor_kernel(PersistState* st, float* part, int NC, int Gs, int nrw, int iters) {
+// The communication skeleton of one sweep with no mat-vec work: tagged column partials through global memory
+// (publish, poll NC words per column), then the row-partial push through distributed shared memory + the cluster
+// barrier.  bench.py times it to state the latency floor of this design next to the measured sweep time.
+__global__ void __cluster_dims__(kT2CS, 1, 1) __launch_bounds__(kT2Threads, 1)
+sinkhorn_tile2d_sync_floor_kernel(PersistState* st, uint32_t* part, int NC, int Gs, int nrw, int iters) {
   extern __shared__ __align__(16) unsigned char smem_raw_t2[];
   float* sm = reinterpret_cast<float*>(smem_raw_t2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = (int)cluster_ctarank(), p = (int)cluster_idx();
-  const unsigned int nb = (unsigned int)(NC * kT2CS);
-  const int nc4 = Gs * 4, rb_pad = kT2Warps * nrw + kT2MaxRowsPerWarp;
+  const int nc4 = Gs * 4, rb_pad = kT2Warps * nrw + kT2MaxRowsPerWarp, W = t2_words(Gs);
   const T2Smem L = t2_carve(nrw, Gs);
   float* u_s = sm + L.u; float* v_s = sm + L.v; float* red_c = sm + L.red_c; float* rowpart = sm + L.rowpart;
   const uint32_t rowpart_saddr = (uint32_t)__cvta_generic_to_shared(rowpart);
-  for (int i = tid; i < kT2Warps * nc4; i += kT2Threads) red_c[i] = 1.0f;
+  for (int i = tid; i < kT2Warps * kT2RedStride; i += kT2Threads) red_c[i] = 1.0f;
   for (int i = tid; i < rb_pad; i += kT2Threads) u_s[i] = 1.0f;
   __syncthreads();
-  unsigned int target = 0;
   for (int it = 0; it < iters; ++it) {
     const int par = it & 1;
+    const uint32_t phase = t2_phase(it);
     __syncthreads();
-    float* my_part = part + ((size_t)(par * kT2CS + q) * NC) * nc4;
+    uint32_t* base = part + ((size_t)(par * kT2CS + q) * NC) * W;
     if (tid < nc4) {
       float s = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < kT2Warps; ++w2) s += red_c[w2 * nc4 + tid];
-      my_part[(size_t)p * nc4 + tid] = s * u_s[0];
-    }
-    t2_grid_barrier(st, target, nb);
-    if (tid < nc4) {
-      float s = 0.f;
-      for (int pp = 0; pp < NC; pp += 16) {
-        float t[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) t[k] = (pp + k < NC) ? ld_relaxed_f32(my_part + (size_t)(pp + k) * nc4 + tid) : 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) s += t[k];
-      }
-      v_s[tid] = 1.0f / s;
+      for (int w2 = 0; w2 < kT2Warps; ++w2) s += red_c[w2 * kT2RedStride + tid];
+      st_signed(base + (size_t)p * W + tid, phase, s * u_s[0]);
+      float tot = 0.f;
+      bool timed_out = false;
+      int never = 0;
+      for (int pp = 0; pp < NC; pp += 16)
+        tot += t2_poll_sum(base + (size_t)pp * W + tid, 4u * (uint32_t)W, min(16, NC - pp), phase, &never, &timed_out);
+      if (timed_out) atomicMax(&st->fallback, 2);
+      v_s[tid] = 1.0f / tot;
     }
     __syncthreads();
     const float tot = v_s[lane];
     const int r = lane & 15;
     if (r < nrw) {
-      const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * rb_pad + warp * nrw + r);
+      const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * kT2RowStride + warp * nrw + r);
       const int q0 = (lane >> 4) * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) st_cluster_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot);
     }
     cluster_sync_all();
     if (tid < kT2Warps * nrw) {
-      const float* rp = rowpart + (par * kT2CS) * rb_pad + tid;
+      const float* rp = rowpart + (par * kT2CS) * kT2RowStride + tid;
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < kT2CS; ++k) s += rp[k * rb_pad];
+      for (int k = 0; k < kT2CS; ++k) s += rp[k * kT2RowStride];
       u_s[tid] = 1.0f / s;
     }
   }
@@ -558,7 +594,7 @@ int sinkhorn_tile2d_absorbs_read() {
 // Co-residency probe: the same launch shape (cluster of 8, 512 threads, the solver's dynamic shared memory) doing
 // ONE grid barrier with a 5 ms budget.  If some cluster cannot be resident together with the others the barrier
 // times out and *ok is cleared — the occupancy query is a necessary condition, this is the sufficient one.
-__global__ void __launch_bounds__(kT2Threads, 1)
+__global__ void __cluster_dims__(kT2CS, 1, 1) __launch_bounds__(kT2Threads, 1)
 t2_probe_kernel(unsigned int* counter, int* ok, unsigned int nblocks) {
   if (threadIdx.x == 0) {
     atomicAdd(counter, 1u);
@@ -592,19 +628,26 @@ static int t2_verified_clusters(PersistState* scratch, cudaStream_t s, int* out)
   const size_t smem = (size_t)max_smem - 1024;
   EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = kT2CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeCooperative;
-  attrs[1].val.cooperative = 1;
+  // The cluster shape is compiled into the kernels (__cluster_dims__), so a launch carries only the cooperative
+  // attribute; the cluster attribute is passed to the occupancy query alone.  (A profiler that re-issues the launch
+  // through the plain cooperative entry point then still gets clusters of 8.)
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = kT2CS; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kT2Threads);
   cfg.stream = s;
   cfg.attrs = attrs;
   cfg.dynamicSmemBytes = smem;
   cfg.gridDim = dim3(kT2CS * kT2MaxClusters);
-  cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cfg.numAttrs = 2;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  }
   n = std::min(n, kT2MaxClusters);
   int verified = -1;
   for (; n >= 4; --n) {
@@ -612,7 +655,7 @@ static int t2_verified_clusters(PersistState* scratch, cudaStream_t s, int* out)
     int one = 1;
     EG_CUDA(cudaMemcpyAsync(&scratch->sweeps, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     cfg.gridDim = dim3((unsigned)(kT2CS * n));
-    cfg.numAttrs = 2;
+    cfg.numAttrs = 1;
     unsigned int nblocks = (unsigned)(kT2CS * n);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, &scratch->barrier, &scratch->sweeps, nblocks);
     if (e != cudaSuccess) { cudaGetLastError(); continue; }          // cooperative launch refused: too many clusters
@@ -638,10 +681,13 @@ static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, PersistS
   if (vrc) return vrc;
   if (verified < 4) return EG_OK;
   g->gs = (int)ceil_div(J / 4, (int64_t)kT2CS);
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = kT2CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeCooperative;
-  attrs[1].val.cooperative = 1;
+  // The cluster shape is compiled into the kernels (__cluster_dims__), so a launch carries only the cooperative
+  // attribute; the cluster attribute is passed to the occupancy query alone.  (A profiler that re-issues the launch
+  // through the plain cooperative entry point then still gets clusters of 8.)
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = kT2CS; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
   *cfg = cudaLaunchConfig_t{};
   cfg->blockDim = dim3(kT2Threads);
   cfg->stream = s;
@@ -652,9 +698,13 @@ static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, PersistS
     EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
     cfg->gridDim = dim3(kT2CS * kT2MaxClusters);
     cfg->dynamicSmemBytes = L.bytes;
-    cfg->numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg) != cudaSuccess) { cudaGetLastError(); return EG_OK; }
+    cfg->numAttrs = 2;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg) != cudaSuccess) {
+      cudaGetLastError();
+      cfg->numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg) != cudaSuccess) { cudaGetLastError(); return EG_OK; }
+    }
     max_clusters = std::min(std::min(max_clusters, kT2MaxClusters), verified);
     if (max_clusters < 4) continue;
     if ((int64_t)max_clusters * kT2Warps * try_nrw >= I) {
@@ -668,12 +718,13 @@ static int t2_geometry(Kern kern, int64_t I, int64_t J, cudaStream_t s, PersistS
   g->rows_per_cluster = (int)ceil_div(I, (int64_t)g->nc);
   cfg->gridDim = dim3((unsigned)(kT2CS * g->nc));
   cfg->dynamicSmemBytes = g->smem;
-  cfg->numAttrs = 2;
+  cfg->numAttrs = 1;
   return EG_OK;
 }
 
-int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* part, size_t part_floats,
+int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, void* part_, size_t part_bytes,
                                       PersistState* st, cudaStream_t s, bool* launched) {
+  uint32_t* part = reinterpret_cast<uint32_t*>(part_);
   *launched = false;
   if (J % 4 != 0 || J > 4 * kT2CS * 32 * kT2QG || iters <= 0) return EG_OK;
   T2Geometry g;
@@ -682,8 +733,10 @@ int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* pa
   auto kern = sinkhorn_tile2d_sync_floor_kernel;
   int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
-  if (g.nc == 0 || (size_t)2 * kT2CS * g.nc * g.gs * 4 > part_floats) return EG_OK;
+  const size_t words = (size_t)2 * kT2CS * g.nc * t2_words(g.gs);
+  if (g.nc == 0 || words * 4 > part_bytes) return EG_OK;
   EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));
+  EG_CUDA(cudaMemsetAsync(part, 0, words * 4, s));               // sign bit 0 everywhere = "not yet published"
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, st, part, g.nc, g.gs, g.nrw, iters);
   if (e != cudaSuccess) { cudaGetLastError(); return EG_OK; }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -693,8 +746,9 @@ int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, float* pa
 
 int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, double inv_reg, const float* a,
                            const float* b, float* log_u, float* log_v, const PersistState* warm, int start_iter,
-                           int max_iter, double stop_thr, float* part, size_t part_floats, PersistState* st,
+                           int max_iter, double stop_thr, void* part_, size_t part_bytes, PersistState* st,
                            float absorb_log2, int force_fallback, cudaStream_t s, bool* launched) {
+  uint32_t* part = reinterpret_cast<uint32_t*>(part_);
   *launched = false;
   if (J % 4 != 0 || (reinterpret_cast<uintptr_t>(M) & 15) || (ld % 4) != 0 || J > 4 * kT2CS * 32 * kT2QG) return EG_OK;
   T2Geometry g;
@@ -703,8 +757,10 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
   auto kern = sinkhorn_tile2d_kernel;
   int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
-  if (g.nc == 0 || (size_t)2 * kT2CS * g.nc * g.gs * 4 > part_floats) return EG_OK;
+  const size_t words = (size_t)2 * kT2CS * g.nc * t2_words(g.gs);
+  if (g.nc == 0 || words * 4 > part_bytes) return EG_OK;
   EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));      // the probe may have used it
+  EG_CUDA(cudaMemsetAsync(part, 0, words * 4, s));               // sign bit 0 everywhere = "not yet published"
   T2Params P;
   P.M = M; P.I = I; P.J = (int)J; P.ld = ld; P.inv2 = inv_reg * 1.4426950408889634074;
   P.a = a; P.b = b; P.log_u = log_u; P.log_v = log_v;

@@ -203,6 +203,11 @@ size_t eg_sinkhorn_dense_workspace_bytes(int dtype, int64_t n_rows, int64_t n_co
  * ws as for eg_sinkhorn_dense(dtype 0).  Timed by the caller: the latency floor bench.py reports next to the
  * measured sweep time.  EG_ERR_UNSUPPORTED when the tile kernel does not take this shape. */
 int eg_sinkhorn_sync_floor(int64_t n_rows, int64_t n_cols, int iters, void* ws, size_t ws_bytes, eg_stream_t stream);
+/* Measurement aid: sustained issue rate of one instruction class on the current device, in lane-operations per second
+ * (kind 0 fp32 FMA, 1 MUFU ex2.approx, 2 fp64 add, 3 fp32 add with |.| — the pattern of the L1 candidate filter).
+ * These are the measured denominators of the SIMT-bound rooflines (SURVEY.md 8d quotes nominal ones; BASELINE.md
+ * section 3 asks for measured).  SYNCHRONOUS (times its own launches with events). */
+int eg_issue_peak(int kind, int iters, double* h_lane_ops_per_s, void* scratch /* device, >= 4 bytes */, eg_stream_t stream);
 
 /* FUSED half-sweep: the cost tile is recomputed from the two embedding sets and
  * reduced straight into the row log-sum-exp; M is never written

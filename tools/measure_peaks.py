@@ -37,3 +37,16 @@ out["how"] = "torch.matmul 8192^3 (allow_tf32 on/off, bf16), best of 10 and 3 s 
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/measured_peaks_extra.json", "w"), indent=1)
+# issue-rate peaks of the SIMT pipes (the denominators of the L1-evaluation and log-domain Sinkhorn rooflines)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+from gnn_mtl_b200 import _lib
+scratch = torch.zeros(4, device=dev)
+for kind, name in ((0, "fp32_fma_lane_ops_per_s"), (1, "mufu_ex2_lane_ops_per_s"), (2, "fp64_add_lane_ops_per_s"),
+                   (3, "fp32_absdiff_add_lane_ops_per_s")):
+    v = C.c_double(0.0)
+    _lib.check(_lib.lib.eg_issue_peak(kind, 2000, C.byref(v), C.c_void_p(scratch.data_ptr()), None), "eg_issue_peak")
+    out[name] = v.value
+out["how_issue"] = "eg_issue_peak: 148 x 8 CTAs x 256 threads, 8 independent chains per thread, best of 3 after a warm-up"
+print(json.dumps(out))
+json.dump(out, open("gpurun_out/measured_peaks_extra.json", "w"), indent=1)
