@@ -82,6 +82,52 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// Remote store that also signals: the 4 bytes land in the peer's shared memory and its mbarrier's transaction count
+// drops by 4 — the receiver waits for "all bytes of this sweep are here" on its OWN barrier, so the row exchange needs
+// neither barrier.cluster nor the release fence in front of it (measured: ERRBAR + arrive + wait = 0.7 us per sweep).
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void t2_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void t2_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool t2_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// ---- tensor memory as the second tier of the tile -------------------------------------------------------------
+// The rows of the tile that do not fit in registers used to live in shared memory: 21 LDS.128 per thread and phase =
+// 0.68 us of shared-memory wavefronts per phase at 128 B/clk.  Tensor memory is idle in this kernel, is private to
+// the CTA, and streams into registers at ~400 B/clk/SM with all 16 warps reading (tools/tmem_bw.cu), so each warp
+// keeps its slow rows in ITS OWN window of TMEM (lanes 32*(warp%4).., 128 columns at 128*(warp/4)): lane = thread,
+// column = 12 floats (3 float4 groups) per row.  Only tcgen05.ld / .st touch it; no other warp ever reads the window.
+constexpr int kT2TmemColsPerRow = kT2QG * 4;
+static_assert(kT2QG == 3 && (kT2MaxRowsPerWarp - kT2RRW + 1) / 2 * 2 * kT2TmemColsPerRow <= 128, "slow rows of a warp must fit its 128-column TMEM window");
+__device__ __forceinline__ void tmem_ld_row_pair(uint32_t taddr, float (&r)[2 * kT2TmemColsPerRow]) {
+  uint32_t x[24];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]) : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[8]), "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]) : "r"(taddr + 8));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[16]), "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]) : "r"(taddr + 16));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 24; ++k) r[k] = __uint_as_float(x[k]);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -168,7 +214,7 @@ __device__ __forceinline__ void scale4(float4& k, float u, const float4& v) {
 }
 
 struct T2Smem {            // offsets in floats into dynamic shared memory
-  int LU, LV, bak_f, bak_g, u, a, v, b, red_c, rowpart, ctrl_in, flags, red_e, kt;
+  int LU, LV, bak_f, bak_g, u, a, v, b, red_c, rowpart, ctrl_in, flags, mbar, red_e, kt;
   size_t bytes;
 };
 __host__ __device__ inline T2Smem t2_carve(int nrw, int gs) {
@@ -186,9 +232,10 @@ __host__ __device__ inline T2Smem t2_carve(int nrw, int gs) {
   s.rowpart = take(2 * kT2CS * kT2RowStride);
   s.ctrl_in = take(2 * kT2CS);                         // [2][kT2CS] marginal-error partials pushed by the cluster peers
   s.flags = take(8);
+  s.mbar = take(4);                                    // two 8-byte mbarriers: row-exchange inbox of even / odd sweeps
   s.kt = take(0);
-  const int srw = nrw > kT2RRW ? nrw - kT2RRW : 0;
-  s.bytes = sizeof(float) * (size_t)off + sizeof(float4) * (size_t)kT2Warps * srw * gs;
+  (void)nrw;
+  s.bytes = sizeof(float) * (size_t)off;          // the tile itself lives in registers + tensor memory
   return s;
 }
 
@@ -225,7 +272,8 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   float* ctrl_in = sm + L.ctrl_in;                       // [2][kT2CS]
   int* flag_s = reinterpret_cast<int*>(sm + L.flags);    // [0] fold v, [1] fold u, [2] bad sum, [3] break code, [4] gave up waiting
   float* ctrl_f = reinterpret_cast<float*>(flag_s + 5);  // [5] total error of the last check (to publish), [6] incoming total
-  float4* kt_s = reinterpret_cast<float4*>(sm + L.kt);   // [warp][SRW][Gs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(flag_s + 7);     // [7] base address of the TMEM allocation
+  const int SRP = (SRW + 1) / 2;                          // slow rows are stored and read two at a time
   const float kAbsorb = P.absorb_log2;
 
   // ---- hand-over: potentials (log2 units), marginals, and the tile of Kt ------------------------------------
@@ -242,7 +290,24 @@ sinkhorn_tile2d_kernel(const T2Params P) {
     b_s[c] = live ? P.b[(int64_t)g_base * 4 + c] : 0.f;
   }
   if (tid < 8) flag_s[tid] = 0;
+  const uint32_t mbar_saddr = (uint32_t)__cvta_generic_to_shared(sm + L.mbar);
+  if (tid == 0) {
+    t2_mbar_init(mbar_saddr, 1);
+    t2_mbar_init(mbar_saddr + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {                             // whole tensor memory of this SM (one CTA per SM, nothing else uses it)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();                          // every peer's inbox barriers exist before anyone can signal them
+  const uint32_t tmem_base = *tmem_slot;
+  // this warp's window: lanes 32*(warp%4).. (the only lanes a warp may address), 128 columns at 128*(warp/4)
+  const uint32_t tmem_w = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
 
   int lg[kT2QG], lgc[kT2QG];
   bool gok[kT2QG];
@@ -272,10 +337,12 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   for (int r = 0; r < kT2RRW; ++r)
 #pragma unroll
     for (int g = 0; g < kT2QG; ++g) kreg[r][g] = (r < nrw) ? build(wrow0 + r, g) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int sr = 0; sr < SRW; ++sr)
+  for (int sr = 0; sr < 2 * SRP; ++sr)           // (the odd row out of the last pair is stored as zeros)
 #pragma unroll
     for (int g = 0; g < kT2QG; ++g)
-      if (lg[g] < Gs) kt_s[(warp * SRW + sr) * Gs + lg[g]] = build(wrow0 + kT2RRW + sr, g);
+      tmem_st4(tmem_w + (uint32_t)(sr * kT2TmemColsPerRow + 4 * g),
+               sr < SRW ? build(wrow0 + kT2RRW + sr, g) : make_float4(0.f, 0.f, 0.f, 0.f));
+  tmem_wait_st();
   __syncthreads();
 
   int cpt = P.start_iter, sweeps = P.start_iter;
@@ -310,8 +377,11 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 
   for (cpt = P.start_iter; cpt < P.max_iter; ++cpt) {
     const int par = cpt & 1;
+    const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     if (timer) t0 = gtime();
+    // this sweep's inbox: 8 peers x (16 warps x nrw rows) floats, + 8 error shares on a checking sweep
+    if (tid == 0) t2_mbar_expect(mbar_saddr + 8u * (uint32_t)par, 4u * (uint32_t)(kT2CS * kT2Warps * nrw + (check ? kT2CS : 0)));
     // ---- C: column partials of my tile (thread: 3 column groups x the warp's rows), packed FMAs ----------------
     {
       Acc4 acc[kT2QG];
@@ -324,15 +394,17 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       for (int r = 0; r < kT2RRW; ++r)
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g) fma4s(acc[g], kreg[r][g], ur[r]);
-      const float4* kw = kt_s + warp * SRW * Gs;
-#pragma unroll 2
-      for (int sr = 0; sr < SRW; ++sr) {
-        const float us = u_s[wrow0 + kT2RRW + sr];
-        float4 k[kT2QG];
+      const float* uw = u_s + wrow0 + kT2RRW;
+#pragma unroll 1
+      for (int sp = 0; sp < SRP; ++sp) {
+        float k[2 * kT2TmemColsPerRow];
+        tmem_ld_row_pair(tmem_w + (uint32_t)(sp * 2 * kT2TmemColsPerRow), k);
+        const float ua = uw[2 * sp], ub = uw[2 * sp + 1];      // (finite even for the padding row; its entries are 0)
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g) k[g] = kw[sr * Gs + lgc[g]];
-#pragma unroll
-        for (int g = 0; g < kT2QG; ++g) fma4s(acc[g], k[g], us);
+        for (int g = 0; g < kT2QG; ++g) {
+          fma4s(acc[g], make_float4(k[4 * g], k[4 * g + 1], k[4 * g + 2], k[4 * g + 3]), ua);
+          fma4s(acc[g], make_float4(k[12 + 4 * g], k[13 + 4 * g], k[14 + 4 * g], k[15 + 4 * g]), ub);
+        }
       }
 #pragma unroll
       for (int g = 0; g < kT2QG; ++g)
@@ -350,7 +422,6 @@ sinkhorn_tile2d_kernel(const T2Params P) {
     // ---- all clusters' partials of MY columns -> v on my slice (every CTA of slice q computes the same bits) ----
     const float s = exchange(cpt, mine, true);
     if (timer) t2 = gtime();
-    const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
     if (check) {   // back-up of the iterate the check refers to (before sweep cpt touches it), as full potentials
       for (int r = tid; r < rb_pad; r += kT2Threads) bak_f[r] = LU_s[r] + log2((double)u_s[r]);
     }
@@ -401,10 +472,20 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       for (int r = 0; r < kT2RRW; ++r)
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g) scale4(kreg[r][g], 1.0f, vq[g]);
-      for (int sr = 0; sr < SRW; ++sr)
+      for (int sp = 0; sp < SRP; ++sp) {
+        float k[2 * kT2TmemColsPerRow];
+        const uint32_t ta = tmem_w + (uint32_t)(sp * 2 * kT2TmemColsPerRow);
+        tmem_ld_row_pair(ta, k);
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g)
-          if (gok[g]) scale4(kt_s[(warp * SRW + sr) * Gs + lg[g]], 1.0f, vq[g]);
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int g = 0; g < kT2QG; ++g) {
+            float4 kk = make_float4(k[12 * h + 4 * g], k[12 * h + 4 * g + 1], k[12 * h + 4 * g + 2], k[12 * h + 4 * g + 3]);
+            scale4(kk, 1.0f, vq[g]);             // vq is 0 on dead groups, and so are their entries
+            tmem_st4(ta + (uint32_t)(12 * h + 4 * g), kk);
+          }
+      }
+      tmem_wait_st();
       if (tid < ncols) { LV_s[tid] += log2((double)v_s[tid]); v_s[tid] = 1.0f; }
       if (tid == 0) { flag_s[0] = 0; if (blockIdx.x == 0) atomicAdd(&g_dev_tile2d_absorbs, 1); }
 #pragma unroll
@@ -423,27 +504,31 @@ sinkhorn_tile2d_kernel(const T2Params P) {
         for (int g = 0; g < kT2QG; ++g) fma4v(d2, kreg[r][g], vq[g]);
         dots[r] = d2.x + d2.y;
       }
-      const float4* kw = kt_s + warp * SRW * Gs;
 #pragma unroll
-      for (int sr = 0; sr < kT2MaxRowsPerWarp - kT2RRW; ++sr) {
-        if (sr < SRW) {
-          float4 k[kT2QG];
+      for (int sp = 0; sp < (kT2MaxRowsPerWarp - kT2RRW) / 2; ++sp) {
+        if (sp < SRP) {                          // warp-uniform
+          float k[2 * kT2TmemColsPerRow];
+          tmem_ld_row_pair(tmem_w + (uint32_t)(sp * 2 * kT2TmemColsPerRow), k);
 #pragma unroll
-          for (int g = 0; g < kT2QG; ++g) k[g] = kw[sr * Gs + lgc[g]];
-          float2 d2 = make_float2(0.f, 0.f);
+          for (int h = 0; h < 2; ++h) {
+            float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int g = 0; g < kT2QG; ++g) fma4v(d2, k[g], vq[g]);
-          dots[kT2RRW + sr] = d2.x + d2.y;
+            for (int g = 0; g < kT2QG; ++g)
+              fma4v(d2, make_float4(k[12 * h + 4 * g], k[12 * h + 4 * g + 1], k[12 * h + 4 * g + 2], k[12 * h + 4 * g + 3]), vq[g]);
+            dots[kT2RRW + 2 * sp + h] = d2.x + d2.y;
+          }
         }
       }
       const float tot = warp_transpose_sum16(dots, lane);
       if (timer) t4 = gtime();
       const int r = lane & 15;
+      const uint32_t inbox_bar = mbar_saddr + 8u * (uint32_t)par;
       if (r < nrw) {
         const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * kT2RowStride + wrow0 + r);
         const int q0 = (lane >> 4) * 4;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) st_cluster_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot);
+        for (int k = 0; k < 4; ++k)
+          st_async_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot, mapa_shared(inbox_bar, (uint32_t)(q0 + k)));
       }
       if (check && tid < kT2CS) {               // my share of the marginal error rides along (zero outside cluster 0)
         double e = 0.0;
@@ -451,10 +536,25 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
           for (int w2 = 0; w2 < kT2Warps; ++w2) e += red_e[w2];
         }
-        st_cluster_f32(mapa_shared(ctrl_saddr + 4u * (uint32_t)(par * kT2CS + q), (uint32_t)tid), (float)e);
+        st_async_f32(mapa_shared(ctrl_saddr + 4u * (uint32_t)(par * kT2CS + q), (uint32_t)tid), (float)e,
+                     mapa_shared(inbox_bar, (uint32_t)tid));
       }
     }
-    cluster_sync_all();
+    // ---- wait for the 8 peers' row partials (and error shares) of this sweep in my own inbox ---------------------
+    if (tid < rb_pad || tid == kT2Threads - 1) {
+      const uint32_t bar = mbar_saddr + 8u * (uint32_t)par;
+      const uint32_t parity = ((uint32_t)(cpt - P.start_iter) >> 1) & 1u;
+      if (!t2_mbar_try(bar, parity)) {
+        const long long tw = clock64();
+        while (!t2_mbar_try(bar, parity)) {
+          if (reinterpret_cast<volatile int*>(flag_s)[4] != 0 || clock64() - tw > kT2WaitClocks) {   // never hang
+            reinterpret_cast<volatile int*>(flag_s)[4] = 1;
+            atomicMax(&st->fallback, 2);
+            break;
+          }
+        }
+      }
+    }
     if (tid < rb_pad) {
       const float* rp = rowpart + (par * kT2CS) * kT2RowStride + tid;
       float rs = 0.f;
@@ -481,12 +581,20 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g) { kreg[r][g].x *= us; kreg[r][g].y *= us; kreg[r][g].z *= us; kreg[r][g].w *= us; }
       }
-      for (int sr = 0; sr < SRW; ++sr) {
-        const float us = u_s[wrow0 + kT2RRW + sr];
+      for (int sp = 0; sp < SRP; ++sp) {
+        float k[2 * kT2TmemColsPerRow];
+        const uint32_t ta = tmem_w + (uint32_t)(sp * 2 * kT2TmemColsPerRow);
+        tmem_ld_row_pair(ta, k);
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g)
-          if (gok[g]) { float4& k = kt_s[(warp * SRW + sr) * Gs + lg[g]]; k.x *= us; k.y *= us; k.z *= us; k.w *= us; }
+        for (int h = 0; h < 2; ++h) {
+          const float us = (2 * sp + h < SRW) ? u_s[wrow0 + kT2RRW + 2 * sp + h] : 0.f;
+#pragma unroll
+          for (int g = 0; g < kT2QG; ++g)
+            tmem_st4(ta + (uint32_t)(12 * h + 4 * g), make_float4(k[12 * h + 4 * g] * us, k[12 * h + 4 * g + 1] * us,
+                                                                 k[12 * h + 4 * g + 2] * us, k[12 * h + 4 * g + 3] * us));
+        }
       }
+      tmem_wait_st();
       __syncthreads();
       if (tid < R) { LU_s[tid] += log2((double)u_s[tid]); u_s[tid] = 1.0f; }
       if (tid == 0) flag_s[1] = 0;
@@ -509,6 +617,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   }
   if (flag_s[2] && tid == 0) atomicMax(&st->fallback, 1);
   __syncthreads();
+  cluster_sync_all();                            // nobody leaves while a peer could still be writing into its inbox
   // ---- outputs (natural-log potentials, composed in fp64) ------------------------------------------------------
   const double ln2 = 0.69314718055994530942;
   if (q == 0) {
@@ -529,27 +638,41 @@ sinkhorn_tile2d_kernel(const T2Params P) {
     st->err = err;
     if (P.force_fallback) atomicMax(&st->fallback, 1);
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-// The communication skeleton of one sweep with no mat-vec work: tagged column partials through global memory
-// (publish, poll NC words per column), then the row-partial push through distributed shared memory + the cluster
-// barrier.  bench.py times it to state the latency floor of this design next to the measured sweep time.
+// The communication skeleton of one sweep with no mat-vec work: sign-tagged column partials through global memory
+// (publish, poll NC words per column), then the row-partial push into the peers' inboxes (st.async + their mbarrier)
+// and the wait on the own inbox.  bench.py times it to state the latency floor of this design next to the measured
+// sweep time.
 __global__ void __cluster_dims__(kT2CS, 1, 1) __launch_bounds__(kT2Threads, 1)
 sinkhorn_tile2d_sync_floor_kernel(PersistState* st, uint32_t* part, int NC, int Gs, int nrw, int iters) {
   extern __shared__ __align__(16) unsigned char smem_raw_t2[];
   float* sm = reinterpret_cast<float*>(smem_raw_t2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = (int)cluster_ctarank(), p = (int)cluster_idx();
+  if (cluster_nctarank() != (uint32_t)kT2CS) { if (tid == 0) atomicMax(&st->fallback, 2); return; }
   const int nc4 = Gs * 4, rb_pad = kT2Warps * nrw + kT2MaxRowsPerWarp, W = t2_words(Gs);
   const T2Smem L = t2_carve(nrw, Gs);
   float* u_s = sm + L.u; float* v_s = sm + L.v; float* red_c = sm + L.red_c; float* rowpart = sm + L.rowpart;
   const uint32_t rowpart_saddr = (uint32_t)__cvta_generic_to_shared(rowpart);
+  const uint32_t mbar_saddr = (uint32_t)__cvta_generic_to_shared(sm + L.mbar);
   for (int i = tid; i < kT2Warps * kT2RedStride; i += kT2Threads) red_c[i] = 1.0f;
   for (int i = tid; i < rb_pad; i += kT2Threads) u_s[i] = 1.0f;
+  if (tid == 0) {
+    t2_mbar_init(mbar_saddr, 1);
+    t2_mbar_init(mbar_saddr + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  cluster_sync_all();
   for (int it = 0; it < iters; ++it) {
     const int par = it & 1;
     const uint32_t phase = t2_phase(it);
+    if (tid == 0) t2_mbar_expect(mbar_saddr + 8u * (uint32_t)par, 4u * (uint32_t)(kT2CS * kT2Warps * nrw));
     __syncthreads();
     uint32_t* base = part + ((size_t)(par * kT2CS + q) * NC) * W;
     if (tid < nc4) {
@@ -568,14 +691,19 @@ sinkhorn_tile2d_sync_floor_kernel(PersistState* st, uint32_t* part, int NC, int 
     __syncthreads();
     const float tot = v_s[lane];
     const int r = lane & 15;
+    const uint32_t inbox_bar = mbar_saddr + 8u * (uint32_t)par;
     if (r < nrw) {
       const uint32_t local = rowpart_saddr + 4u * (uint32_t)((par * kT2CS + q) * kT2RowStride + warp * nrw + r);
       const int q0 = (lane >> 4) * 4;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) st_cluster_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot);
+      for (int k = 0; k < 4; ++k)
+        st_async_f32(mapa_shared(local, (uint32_t)(q0 + k)), tot, mapa_shared(inbox_bar, (uint32_t)(q0 + k)));
     }
-    cluster_sync_all();
     if (tid < kT2Warps * nrw) {
+      const uint32_t parity = ((uint32_t)it >> 1) & 1u;
+      const long long tw = clock64();
+      while (!t2_mbar_try(inbox_bar, parity))
+        if (clock64() - tw > kT2WaitClocks) { atomicMax(&st->fallback, 2); break; }
       const float* rp = rowpart + (par * kT2CS) * kT2RowStride + tid;
       float s = 0.f;
 #pragma unroll
@@ -583,6 +711,8 @@ sinkhorn_tile2d_sync_floor_kernel(PersistState* st, uint32_t* part, int NC, int 
       u_s[tid] = 1.0f / s;
     }
   }
+  __syncthreads();
+  cluster_sync_all();
 }
 
 int sinkhorn_tile2d_absorbs_read() {
