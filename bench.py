@@ -600,7 +600,8 @@ def run_ours(args):
             floor_us = None
         sm_clk = 1.965e9
         fma_floor_us = 2.0 * I_ * J_ / (148 * 128 * sm_clk) * 1e6          # 2 mat-vecs, one FMA per entry
-        smem_floor_us = 2.0 * (I_ * J_ * 4.0 * 0.5) / (148 * 128 * sm_clk) * 1e6   # ~half of the tile lives in shared memory
+        # 7 of a warp's 13 rows stream from tensor memory twice per sweep, ~400 B/clk/SM measured (tools/tmem_bw.cu)
+        tmem_floor_us = 2.0 * (I_ * J_ * 4.0 * 7.0 / 13.0) / (120 * 400 * sm_clk) * 1e6
         sk_block = {"kernel": "sinkhorn_tile2d_kernel (scaling-domain sweeps, kernel matrix tiled over 8-CTA clusters "
                               "x column slices, on chip for the whole solve) after a 4-sweep log-domain warm-up launch; "
                               "timed together, %d sweeps" % sw,
@@ -608,13 +609,16 @@ def run_ours(args):
                     "exchange_floor_us_per_sweep": floor_us,
                     "frac_of_exchange_floor": (floor_us / us_sweep) if floor_us else None,
                     "fp32_issue_floor_us_per_sweep": fma_floor_us, "frac_fp32_issue": fma_floor_us / us_sweep,
-                    "smem_bandwidth_floor_us_per_sweep": smem_floor_us,
+                    "tmem_stream_floor_us_per_sweep": tmem_floor_us,
                     "launches_timed": len(sk_ms),
                     "share_of_step": (sum(sk_ms) / min(K, 5)) / step_ms_instr,
                     "hbm_equivalent_gbs_note": 2.0 * sw * I_ * J_ * 4 / 1e9 / (ms_solve / 1e3),
-                    "note": "one grid barrier + one cluster barrier per sweep; exchange_floor = the same launch doing "
-                            "only that exchange (eg_sinkhorn_sync_floor), i.e. what no amount of mat-vec tuning "
-                            "removes. hbm_equivalent = bytes a streaming solver would move; not a roofline."}
+                    "note": "per sweep: column partials published as sign-tagged words and polled by their consumers "
+                            "(one L2 round trip, no grid barrier), row partials pushed into the 8 cluster peers' "
+                            "shared memory with st.async + mbarrier (no cluster barrier); tile = registers + tensor "
+                            "memory. exchange_floor = the same launch doing only that exchange "
+                            "(eg_sinkhorn_sync_floor), i.e. what no amount of mat-vec tuning removes. "
+                            "hbm_equivalent = bytes a streaming solver would move; not a roofline."}
         try:
             sk_block["log_domain_redos_in_run"] = int(_lib.lib.eg_debug_set(8, 0))
         except Exception:    # noqa: BLE001

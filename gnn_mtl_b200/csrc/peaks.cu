@@ -17,17 +17,17 @@ __global__ void __launch_bounds__(256) issue_probe_kernel(float* sink, int iters
   double d[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { x[k] = seed + (float)(threadIdx.x + k) * 1e-3f; d[k] = (double)x[k]; }
-  const float a = 0.999f + seed * 1e-6f, b = 1e-3f;
+  const float a = 1e-9f * seed;
   const double db = 1e-9 * (double)seed;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (KIND == 0) x[k] = fmaf(x[k], a, b);
+        if (KIND == 0) x[k] = fmaf(x[k], a, x[k]);     // two distinct source registers: no bank conflict on the operand fetch
         else if (KIND == 1) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
         else if (KIND == 2) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[k]) : "d"(db));
-        else x[k] += fabsf(x[k] - a);
+        else x[k] += fabsf(x[k] - 0.999f);
       }
     }
   }

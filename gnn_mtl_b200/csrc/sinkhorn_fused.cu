@@ -29,7 +29,7 @@ int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, c
 
 int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_hi, const float* A2_lo, int k2p,
                int64_t m, const float* B_hi, const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1,
-               int64_t n1, float* out2, int64_t ld2, cudaStream_t s);
+               int64_t n1, float* out2, int64_t ld2, int flush, cudaStream_t s);
 
 constexpr int kFT = 64;    // tile edge
 constexpr int kFK = 16;    // k-chunk
@@ -352,7 +352,20 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad, const 
   if (m == 0) return EG_OK;
   if (!A1_hi || !A1_lo || !B_hi || !B_lo || !out1) return EG_ERR_INVALID;
   if (k2_pad > 0 && (!A2_hi || !A2_lo)) return EG_ERR_INVALID;
-  return gemm_nt_tc(A1_hi, A1_lo, k1_pad, A2_hi, A2_lo, k2_pad, m, B_hi, B_lo, n, bias, out1, ld1, n1, out2, ld2,
+  return gemm_nt_tc(A1_hi, A1_lo, k1_pad, A2_hi, A2_lo, k2_pad, m, B_hi, B_lo, n, bias, out1, ld1, n1, out2, ld2, 0,
+                    as_stream(stream_));
+}
+
+int eg_gemm_nt_3xtf32_chained(const float* A1_hi, const float* A1_lo, int k1_pad, const float* A2_hi,
+                              const float* A2_lo, int k2_pad, int64_t m, const float* B_hi, const float* B_lo,
+                              int64_t n, const float* bias, float* out1, int64_t ld1, int64_t n1, float* out2,
+                              int64_t ld2, eg_stream_t stream_) {
+  using namespace eg;
+  if (m < 0 || n <= 0) return EG_ERR_INVALID;
+  if (m == 0) return EG_OK;
+  if (!A1_hi || !A1_lo || !B_hi || !B_lo || !out1) return EG_ERR_INVALID;
+  if (k2_pad > 0 && (!A2_hi || !A2_lo)) return EG_ERR_INVALID;
+  return gemm_nt_tc(A1_hi, A1_lo, k1_pad, A2_hi, A2_lo, k2_pad, m, B_hi, B_lo, n, bias, out1, ld1, n1, out2, ld2, 1,
                     as_stream(stream_));
 }
 

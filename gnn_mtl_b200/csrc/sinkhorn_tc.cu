@@ -121,6 +121,13 @@ struct Params {
 // MODE 0: per-row online log-sum-exp of  pot_in[j] - cost*inv_reg          -> part_m / part_s
 // MODE 1: plan statistics with P_ij = exp(pot_a[i] + pot_in[j] - cost*inv_reg) -> loss, row_sum
 // MODE 2: plain 3xTF32 GEMM  C = [A1 | A2] · Bᵀ + bias  (pot_in carries the bias)   -> out1 / out2
+// MODE 3: the same GEMM with SHORT ACCUMULATION CHAINS: the tensor core truncates on every accumulate (~3e-8 relative
+//         per MMA, a one-sided bias that grows with the chain: 2e-6 over the 114 MMAs of K = 304), so here every
+//         k-block (6 MMAs) starts a fresh TMEM accumulator and the epilogue warps add the finished block into fp32
+//         registers (round-to-nearest) while the next block runs in the other buffer.  Error ~3e-7: the level of an
+//         fp32 SIMT product, which is what a ReLU-feeding product needs (layers/layers.py:32,61 feed F.relu).
+//         Column tile <= kFlushBN so that a thread's row of accumulators stays in registers.
+constexpr int kFlushBN = 160;
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -140,7 +147,8 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.x * BM;
-  const int bn = (MODE == 2) ? p.bn : BN;                 // UMMA N of this launch
+  constexpr bool GEMM = (MODE >= 2);
+  const int bn = GEMM ? p.bn : BN;                        // UMMA N of this launch
   const int n_btiles = (int)((p.nB + bn - 1) / bn);
   const int t_begin = blockIdx.y * p.tiles_per_split;
   const int t_end = min(n_btiles, t_begin + p.tiles_per_split);
@@ -148,12 +156,12 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   // row tiles blockIdx.x, blockIdx.x + gridDim.x, ... and all column tiles of each, as one continuous pipeline
   // (a 3-tile CTA spent a third of its life in prologue and the un-overlapped last epilogue).
   const int n_rtiles = (int)((p.nA + BM - 1) / BM);
-  const int my_rtiles = (MODE == 2) ? (n_rtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
-  const int n_tiles = (MODE == 2) ? my_rtiles * n_btiles : max(t_end - t_begin, 0);
+  const int my_rtiles = GEMM ? (n_rtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  const int n_tiles = GEMM ? my_rtiles * n_btiles : max(t_end - t_begin, 0);
   auto tile_i0 = [&](int t) -> int64_t {
-    return (MODE == 2) ? ((int64_t)blockIdx.x + (int64_t)(t / n_btiles) * gridDim.x) * BM : i0;
+    return GEMM ? ((int64_t)blockIdx.x + (int64_t)(t / n_btiles) * gridDim.x) * BM : i0;
   };
-  auto tile_j0 = [&](int t) -> int { return (MODE == 2) ? (t % n_btiles) * bn : (t_begin + t) * BN; };
+  auto tile_j0 = [&](int t) -> int { return GEMM ? (t % n_btiles) * bn : (t_begin + t) * BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -181,7 +189,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = stage_base + s * STAGE_BYTES;
           mbar_expect_tx(&full[s], 2 * A_TILE_BYTES + 2 * bn * BK * 4);   // the B boxes are bn rows tall
-          if (MODE != 2 || kb < p.kb_split) {
+          if (!GEMM || kb < p.kb_split) {
             tma_load_2d(st, &map_a_hi, &full[s], kb * BK, ti0);
             tma_load_2d(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, ti0);
           } else {
@@ -199,13 +207,22 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, bn);
       int s = 0; uint32_t ph = 0;
+      uint32_t chain = 0;                                  // MODE 3: accumulation chains issued so far
       for (int t = 0; t < n_tiles; ++t) {
-        const int buf = t & 1;
-        const uint32_t use = (uint32_t)(t >> 1);           // how many times this buffer was used before
-        mbar_wait(&tempty[buf], (use & 1) ^ 1);            // epilogue has drained the buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        int buf = t & 1;
+        uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        if (MODE != 3) {
+          const uint32_t use = (uint32_t)(t >> 1);         // how many times this buffer was used before
+          mbar_wait(&tempty[buf], (use & 1) ^ 1);          // epilogue has drained the buffer
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (MODE == 3) {                                 // a fresh accumulator per k-block, buffers alternate
+            buf = (int)(chain & 1u);
+            tmem_d = tmem_base + (uint32_t)(buf * BN);
+            mbar_wait(&tempty[buf], ((chain >> 1) & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
           mbar_wait(&full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(stage_base + s * STAGE_BYTES);
@@ -219,14 +236,15 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           for (int k = 0; k < BK / UK; ++k) {
             if (k >= k_steps) break;
             const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);   // 32 B per k-step, in 16-byte units
-            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, MODE == 3 ? (uint32_t)(k != 0) : (uint32_t)((kb | k) != 0));
             umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
             umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
           }
           umma_commit(&empty[s]);                           // smem stage reusable once these MMAs retire
+          if (MODE == 3) { umma_commit(&tfull[buf]); ++chain; }    // chain complete: the epilogue folds it
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[buf]);                           // accumulator complete
+        if (MODE != 3) umma_commit(&tfull[buf]);            // accumulator complete
       }
     }
   } else {
@@ -235,9 +253,9 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;
     const int64_t row = i0 + row_in_tile;
-    const float na = (MODE != 2 && row < p.nA) ? p.normA[row] : 0.f;
+    const float na = (!GEMM && row < p.nA) ? p.normA[row] : 0.f;
     const float fa = (MODE == 1 && row < p.nA) ? p.pot_a[row] : -CUDART_INF_F;
-    const bool near_ok = (MODE != 2) && row < p.nA && p.A_raw != nullptr && p.B_raw != nullptr;
+    const bool near_ok = (!GEMM) && row < p.nA && p.A_raw != nullptr && p.B_raw != nullptr;
     float run_m = -CUDART_INF_F, run_s = 0.f;
     double loss_acc = 0.0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -248,12 +266,49 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       float2* ci = colinfo + buf * BN;
       for (int c = ep_tid; c < BN; c += 128) {
         int64_t j = j0 + c;
-        if (MODE == 2)
+        if (GEMM)
           ci[c] = make_float2(0.f, (j < p.nB && p.pot_in) ? p.pot_in[j] : 0.f);
         else
           ci[c] = (j < p.nB) ? make_float2(p.normB[j], p.pot_in[j]) : make_float2(0.f, -CUDART_INF_F);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (MODE == 3) {
+        float accf[kFlushBN];
+#pragma unroll
+        for (int c = 0; c < kFlushBN; ++c) accf[c] = 0.f;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const uint32_t chain = (uint32_t)t * (uint32_t)p.k_blocks + (uint32_t)kb;
+          const int cb = (int)(chain & 1u);
+          mbar_wait(&tfull[cb], (chain >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN);
+#pragma unroll
+          for (int c0 = 0; c0 < kFlushBN; c0 += 32) {
+            if (c0 < bn) {                                   // CTA-uniform
+              float dot[32];
+              tmem_ld32(ta + (uint32_t)c0, dot);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) accf[c0 + c] += dot[c];
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[cb]);
+        }
+        if (trow < p.nA) {
+#pragma unroll
+          for (int c = 0; c < kFlushBN; c += 4) {
+            const int64_t j = j0 + c;
+            if (c < bn && j < p.nB) {                        // nB, n1, bn are multiples of 4 (checked on the host)
+              const float4 v = make_float4(accf[c] + ci[c].y, accf[c + 1] + ci[c + 1].y, accf[c + 2] + ci[c + 2].y,
+                                           accf[c + 3] + ci[c + 3].y);
+              float* dst = (j < p.n1) ? p.out1 + trow * p.ld1 + j : p.out2 + trow * p.ld2 + (j - p.n1);
+              *reinterpret_cast<float4*>(dst) = v;
+            }
+          }
+        }
+        continue;
+      }
       mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
@@ -302,7 +357,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         // rare and warp-uniform: lanes that found close pairs in this chunk take turns; for each such pair the
         // WHOLE warp re-evaluates it from the fp32 rows (exact_pair_warp) and the owner patches its z
-        unsigned owners = (MODE != 2) ? __ballot_sync(0xffffffffu, near_ok && near_min < 0.f) : 0u;
+        unsigned owners = (!GEMM) ? __ballot_sync(0xffffffffu, near_ok && near_min < 0.f) : 0u;
         while (owners) {
           const int src = __ffs(owners) - 1;
           owners &= owners - 1;
@@ -531,7 +586,7 @@ int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, c
 // splits (eg_split_tf32) with every K extent padded to a multiple of 16 (= one k-block).
 int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_hi, const float* A2_lo, int k2p,
                int64_t m, const float* B_hi, const float* B_lo, int64_t n, const float* bias, float* out1, int64_t ld1,
-               int64_t n1, float* out2, int64_t ld2, cudaStream_t s) {
+               int64_t n1, float* out2, int64_t ld2, int flush, cudaStream_t s) {
   using namespace tc;
   if (k1p <= 0 || k1p % BK || k2p < 0 || k2p % BK || n % 4 || n1 % 4 || n1 > n || n1 <= 0) return EG_ERR_INVALID;
   if (n1 < n && !out2) return EG_ERR_INVALID;
@@ -550,8 +605,10 @@ int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_
     L.ma2_lo = L.ma_lo;
   }
   // column tile: as few tiles as BN = 256 allows, each just wide enough (multiple of 16): n = 300 -> 2 x 160, not 2 x 256
-  const int64_t n_ct = ceil_div(n, (int64_t)BN);
-  const int bn = (int)std::min<int64_t>(BN, ceil_div(ceil_div(n, n_ct), (int64_t)16) * 16);
+  // (flush: short accumulation chains folded in registers, MODE 3 — the tile is capped so a row of sums fits)
+  const int64_t bn_cap = flush ? kFlushBN : BN;
+  const int64_t n_ct = ceil_div(n, bn_cap);
+  const int bn = (int)std::min<int64_t>(bn_cap, ceil_div(ceil_div(n, n_ct), (int64_t)16) * 16);
   if ((rc = make_map(&L.mb_hi, B_hi, n, kp, bn))) return rc;
   if ((rc = make_map(&L.mb_lo, B_lo, n, kp, bn))) return rc;
   Params& p = L.p;
@@ -560,11 +617,16 @@ int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_
   p.pot_in = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
   p.bn = bn;
   p.tiles_per_split = (int)ceil_div(n, (int64_t)bn);
-  static PerDeviceOnce attr_once2;
+  static PerDeviceOnce attr_once2, attr_once3;
   EG_SET_SMEM_ONCE(attr_once2,
                    EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+  EG_SET_SMEM_ONCE(attr_once3,
+                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(m, BM), kNumSMs), 1);    // persistent over row tiles
-  lse_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
+  if (flush)
+    lse_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
+  else
+    lse_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
   EG_LAUNCHED();
   return EG_OK;
 }

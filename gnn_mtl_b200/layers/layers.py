@@ -98,6 +98,7 @@ class _Aggregate(torch.autograd.Function):
 
 USE_TCGEN05_GEMM = True   # dense layer products on the 3xTF32 tcgen05 tiles; False -> everything on cuBLAS fp32
 USE_TCGEN05_DW = True     # dW = dHᵀ·x on the MN-major split-K tcgen05 kernel; False -> cuBLAS fp32 batched split-K
+USE_CHAINED_GEMM = True   # ReLU-feeding x·Wᵀ + b on the short-chain tcgen05 kernel; False -> cuBLAS fp32 (SIMT)
 
 
 def _weight_grad(d_hidden, x):
@@ -130,7 +131,17 @@ class _DenseProducts(torch.autograd.Function):
         n_out = weight.shape[0]
         gate_pre = None
         x_split = None                      # hi/lo split of x: made once, reused by dW = dHᵀ·x in backward
-        if exact_hidden:
+        if exact_hidden and USE_CHAINED_GEMM:
+            # short accumulation chains (6 MMAs, folded in fp32 registers): fp32-SIMT-level error, so the ReLU
+            # behind the aggregation sees the same branches as an fp32 product; gate_pre rides in the same launch
+            if gate_w is None:
+                hidden, sp = ops.gemm_nt([x], weight, bias, return_splits=True, chained=True)
+            else:
+                b0 = bias if bias is not None else torch.zeros(n_out, device=x.device)
+                (hidden, gate_pre), sp = ops.gemm_nt([x], torch.cat([weight, gate_w.t()], 0), torch.cat([b0, gate_b]),
+                                                     n1=n_out, return_splits=True, chained=True)
+            x_split = sp[0]
+        elif exact_hidden:
             # cuBLAS fp32; the bias is added in place afterwards (cublasLt's own bias pass for this shape is a
             # separate 0.34 ms kernel, the in-place add 0.16 ms; same roundings: fl(fl(x·Wᵀ) + b))
             hidden = torch.mm(x, weight.t())

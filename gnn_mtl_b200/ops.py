@@ -409,8 +409,10 @@ def gemm_tn(a_split, m, b_split, n):
     return out
 
 
-def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False):
+def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False, chained=False):
     """C = [A1 | A2 ...] · Bᵀ + bias with fp32 accuracy (3xTF32 on tcgen05).
+    ``chained=True``: short accumulation chains folded in fp32 registers (eg_gemm_nt_3xtf32_chained): ~3e-7 relative
+    instead of ~2e-6 — for products whose result decides a ReLU branch.
     A_parts: one or two [m, k_i] fp32 CUDA tensors; B: [n, sum k_i] fp32 (row j = output column j).
     Returns out1 [m, n1] (and out2 [m, n - n1] when n1 < n).  ``a_splits``: reuse hi/lo pairs computed earlier
     (one per A part, padded to 16 columns); ``return_splits=True`` appends the list of pairs used."""
@@ -442,10 +444,11 @@ def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False):
     a2_hi, a2_lo = (splits[1] if len(splits) == 2 else (None, None))
     bias = _f32c(bias) if bias is not None else None
     with torch.cuda.device(dev):
-        check(lib.eg_gemm_nt_3xtf32(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
-                                    _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
-                                    ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
-              "eg_gemm_nt_3xtf32")
+        fn = lib.eg_gemm_nt_3xtf32_chained if chained else lib.eg_gemm_nt_3xtf32
+        check(fn(ptr(splits[0][0]), ptr(splits[0][1]), _pad16(ks[0]), ptr(a2_hi), ptr(a2_lo),
+                 _pad16(ks[1]) if len(ks) == 2 else 0, m, ptr(b_hi), ptr(b_lo), n, ptr(bias),
+                 ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
+              "eg_gemm_nt_3xtf32_chained" if chained else "eg_gemm_nt_3xtf32")
     res = (out1, out2) if out2 is not None else out1
     return (res, splits) if return_splits else res
 

@@ -260,6 +260,14 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
                       const float* A2_hi, const float* A2_lo, int k2_pad, int64_t m,
                       const float* B_hi, const float* B_lo, int64_t n, const float* bias,
                       float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
+/* Same product with SHORT ACCUMULATION CHAINS (a fresh tensor-memory accumulator every 6 MMAs, folded into fp32
+ * registers): ~3e-7 relative instead of ~2e-6, i.e. the accuracy of an fp32 SIMT product.  For the products
+ * that feed a ReLU through the aggregation (layers/layers.py:32-38, 61-64), where a 2e-6 error flips the sign of
+ * too many near-zero pre-activations for gradient parity. */
+int eg_gemm_nt_3xtf32_chained(const float* A1_hi, const float* A1_lo, int k1_pad,
+                              const float* A2_hi, const float* A2_lo, int k2_pad, int64_t m,
+                              const float* B_hi, const float* B_lo, int64_t n, const float* bias,
+                              float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
 
 
 /* Weight gradient of those products: C[m, n] = sum_k A[k, m] * B[k, n]  (dW = dH^T x; K = #entities).

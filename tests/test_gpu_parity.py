@@ -540,6 +540,36 @@ def test_gemm_nt_3xtf32_matches_fp64(m, k, n, n1, dev):
     assert relerr(got2, ref2) < 1e-5
 
 
+@pytest.mark.parametrize("m,k,n,n1", [(1000, 300, 300, 300), (4099, 300, 600, 300), (257, 128, 128, 128),
+                                      (130, 52, 340, 20), (200000, 300, 300, 300)])
+def test_gemm_nt_chained_is_fp32_accurate(m, k, n, n1, dev):
+    """Short-chain variant (eg_gemm_nt_3xtf32_chained, the ReLU-feeding x·Wᵀ + b of layers/layers.py:32,61):
+    error at the level of an fp32 SIMT product (cuBLAS fp32 on the same operands is the yardstick), several times
+    below the long-chain kernel's."""
+    from gnn_mtl_b200 import ops
+    torch.manual_seed(m + n)
+    A = torch.randn(m, k, device=dev)
+    B = torch.randn(n, k, device=dev) * 0.1
+    bias = torch.randn(n, device=dev)
+    ref = A.double() @ B.double().t() + bias.double()
+    res = ops.gemm_nt([A], B, bias, n1=n1, chained=True)
+    got = torch.cat(res, 1) if isinstance(res, tuple) else res
+    plain = ops.gemm_nt([A], B, bias, n1=n1)
+    plain = torch.cat(plain, 1) if isinstance(plain, tuple) else plain
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        simt = torch.addmm(bias, A, B.t())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    e_chain, e_plain, e_simt = relerr(got, ref), relerr(plain, ref), relerr(simt, ref)
+    print("m=%d k=%d n=%d: chained %.2e  long-chain %.2e  cuBLAS fp32 %.2e" % (m, k, n, e_chain, e_plain, e_simt))
+    assert e_chain < 5e-7
+    assert e_chain < max(2.0 * e_simt, 2e-7)
+    # mean absolute error too (the long chain's error is a one-sided bias; the short chain's must not be)
+    assert float((got.double() - ref).mean().abs()) < 3e-7 * float(ref.abs().mean()) + 1e-9
+
+
 def test_margin_loss_golden_and_scale(golden_dir, dev):
     """Fused gather + L1 + hinge loss (models/models_ea.py:103-123): value and gradient."""
     from oracle import ea_oracle as orc

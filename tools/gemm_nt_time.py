@@ -20,3 +20,13 @@ for n in (600, 300):
     t = timed(lambda: ops.gemm_nt([x], W, b, n1=300 if n == 600 else None, a_splits=sp))
     print("gemm_nt m=%d k=%d n=%d: %.3f ms  (%.0f TF/s TF32-MMA, %.0f fp32-equivalent; writes %.0f MB)"
           % (m, k, n, t, 3 * 2.0 * m * n * 304 / t / 1e9, 2.0 * m * n * k / t / 1e9, m * n * 4 / 1e6), flush=True)
+
+# short-chain (ReLU-feeding) variant and the cuBLAS fp32 product it replaces
+for n in (600, 300):
+    W = torch.randn(n, k, device=dev) / 17; b = torch.randn(n, device=dev)
+    t = timed(lambda: ops.gemm_nt([x], W, b, n1=300 if n == 600 else None, a_splits=sp, chained=True))
+    print("gemm_nt CHAINED m=%d k=%d n=%d: %.3f ms  (%.0f TF/s TF32-MMA)" % (m, k, n, t, 3 * 2.0 * m * n * 304 / t / 1e9), flush=True)
+W = torch.randn(300, k, device=dev) / 17; b = torch.randn(300, device=dev)
+torch.backends.cuda.matmul.allow_tf32 = False
+t = timed(lambda: torch.mm(x, W.t()).add_(b))
+print("cuBLAS fp32 mm + bias m=%d k=%d n=300: %.3f ms" % (m, k, t), flush=True)
