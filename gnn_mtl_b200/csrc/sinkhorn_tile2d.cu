@@ -57,7 +57,7 @@ struct T2Params {
   float absorb_log2; int force_fallback;
 };
 // words one CTA publishes per sweep: its column partials + one control word (total marginal error of the last check)
-__host__ __device__ inline int t2_words(int gs) { return gs * 4 + 4; }
+__host__ __device__ inline int t2_words(int /*gs*/) { return kT2QG * 32 * 4 + 4; }   // compile-time: poll addresses are immediates
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -142,37 +142,37 @@ __device__ __forceinline__ void st_signed(uint32_t* p, uint32_t phase, float v) 
   const uint32_t w = (__float_as_uint(v) & 0x7fffffffu) | (phase << 31);
   asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
 }
-// predicated load (no branch around it: the 16 polls of a round issue back to back)
-__device__ __forceinline__ void ld_signed_if(uint32_t& w, const char* p, uint32_t pred) {
-  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %2, 0;\n\t@pp ld.relaxed.gpu.global.b32 %0, [%1];\n\t}"
-               : "+r"(w) : "l"(p), "r"(pred) : "memory");
-}
-// Polls up to 16 words `stride_bytes` apart until each carries `phase`; returns their sum in index order (fixed order
-// -> every CTA that adds the same words gets the same bits).  Gives up (sum of what arrived) when `*give_up` is set or
-// after kT2WaitClocks, and reports that through *timed_out.
-__device__ __forceinline__ float t2_poll_sum(const uint32_t* src, uint32_t stride_bytes, int n, uint32_t phase,
-                                             volatile int* give_up, bool* timed_out) {
-  uint32_t w[16];
-  uint32_t pend = (n >= 16) ? 0xffffu : ((1u << n) - 1u);
+// Polls N words `kT2PartStride` apart until each carries `phase`; returns their sum in index order (fixed order
+// -> every CTA that adds the same words gets the same bits).  N is always 16: the rows of clusters that do not exist
+// (NC..15) are published as zeros by the last cluster, so the loop needs no per-word predicate.  All N loads of a round issue back to back from one
+// base register (immediate offsets); a round that finds a stale word is simply repeated (a word, once valid, stays
+// valid until its reader has moved on).  Gives up (sum of what arrived) when `*give_up` is set or after
+// kT2WaitClocks, and reports that through *timed_out.
+constexpr int kT2PartStride = kT2QG * 32 * 4 + 4;
+template <int N>
+__device__ __forceinline__ float t2_poll_sum(const uint32_t* src, uint32_t phase, volatile int* give_up, bool* timed_out) {
+  uint32_t w[N];
   const uint32_t want = phase << 31;
-  const char* p0 = reinterpret_cast<const char*>(src);
-#pragma unroll
-  for (int k = 0; k < 16; ++k) w[k] = want ^ 0x80000000u;
   long long t0 = 0;
   while (true) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) ld_signed_if(w[k], p0 + (size_t)((uint32_t)k * stride_bytes), (pend >> k) & 1u);
+    for (int k = 0; k < N; ++k)
+      asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(w[k]) : "l"(src + (size_t)k * kT2PartStride) : "memory");
+    uint32_t bad = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      if (((w[k] ^ want) >> 31) == 0u) pend &= ~(1u << k);
-    if (pend == 0) break;
+    for (int k = 0; k < N; ++k) bad |= w[k] ^ want;
+    if ((bad >> 31) == 0u) break;
     if (t0 == 0) t0 = clock64();
-    if (*give_up != 0 || clock64() - t0 > kT2WaitClocks) { *timed_out = true; break; }
+    if (*give_up != 0 || clock64() - t0 > kT2WaitClocks) {      // never hang: stale words count as 0
+      *timed_out = true;
+#pragma unroll
+      for (int k = 0; k < N; ++k) if (((w[k] ^ want) >> 31) != 0u) w[k] = 0u;
+      break;
+    }
   }
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
-    if (k < n && !((pend >> k) & 1u)) s += __uint_as_float(w[k] & 0x7fffffffu);
+  for (int k = 0; k < N; ++k) s += fabsf(__uint_as_float(w[k]));     // published values are >= 0
   return s;
 }
 
@@ -357,16 +357,25 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   // columns.  Returns the cluster-order sum for thread `tid` (< nc4); thread nc4 fetches the control word of cluster 0.
   auto exchange = [&](int sweep, float mine, bool publish_partials) -> float {
     const uint32_t phase = t2_phase(sweep - P.start_iter);
-    uint32_t* base = P.part + ((size_t)((sweep & 1) * kT2CS + q) * NC) * W;
-    if (tid < nc4) { if (publish_partials) st_signed(base + (size_t)p * W + tid, phase, mine); }
-    else if (tid == nc4) st_signed(base + (size_t)p * W + nc4, phase, ctrl_f[0]);
+    uint32_t* base = P.part + ((size_t)((sweep & 1) * kT2CS + q) * ((NC + 15) & ~15)) * W;
+    const int NCP = (NC + 15) & ~15;                       // rows polled per column
+    if (tid < nc4) {
+      if (publish_partials) {
+        st_signed(base + (size_t)p * W + tid, phase, mine);
+        if (p == NC - 1)                                   // the rows of the clusters that do not exist read as +0
+          for (int pp = NC; pp < NCP; ++pp) st_signed(base + (size_t)pp * W + tid, phase, 0.f);
+      }
+    } else if (tid == nc4) st_signed(base + (size_t)p * W + nc4, phase, ctrl_f[0]);
     float s = 0.f;
     if ((publish_partials && tid < nc4) || tid == nc4) {
-      const int n_src = (tid == nc4) ? 1 : NC;             // the control word comes from cluster 0 only
       bool timed_out = false;
-      for (int pp = 0; pp < n_src; pp += 16)
-        s += t2_poll_sum(base + (size_t)pp * W + tid, 4u * (uint32_t)W, min(16, n_src - pp), phase,
-                         reinterpret_cast<volatile int*>(flag_s) + 4, &timed_out);
+      volatile int* give_up = reinterpret_cast<volatile int*>(flag_s) + 4;
+      if (tid == nc4) {                                    // the control word comes from cluster 0 only
+        s = t2_poll_sum<1>(base + tid, phase, give_up, &timed_out);
+      } else {
+        for (int pp = 0; pp < NCP; pp += 16)
+          s += t2_poll_sum<16>(base + (size_t)pp * W + tid, phase, give_up, &timed_out);
+      }
       if (timed_out && reinterpret_cast<volatile int*>(flag_s)[4] == 0) {      // never hang: the host redoes the solve
         reinterpret_cast<volatile int*>(flag_s)[4] = 1;
         atomicMax(&st->fallback, 2);
@@ -438,7 +447,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
           }
         }
         if (live) {
-          const float vn = b_s[tid] / s;
+          const float vn = __fdividef(b_s[tid], s);       // every CTA of the slice runs the same instructions: same bits
           if (!(s > 0.f) || !(vn < CUDART_INF_F) || !(vn > 0.f)) flag_s[2] = 1;
           if (fabsf(lg2f(vn)) > kAbsorb) flag_s[0] = 1;
           v_s[tid] = vn;
@@ -561,7 +570,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
       for (int k = 0; k < kT2CS; ++k) rs += rp[k * kT2RowStride];
       if (tid < R) {
-        const float un = a_s[tid] / rs;
+        const float un = __fdividef(a_s[tid], rs);
         if (!(rs > 0.f) || !(un < CUDART_INF_F) || !(un > 0.f)) flag_s[2] = 1;
         if (fabsf(lg2f(un)) > kAbsorb) flag_s[1] = 1;
         u_s[tid] = un;
@@ -674,17 +683,20 @@ sinkhorn_tile2d_sync_floor_kernel(PersistState* st, uint32_t* part, int NC, int 
     const uint32_t phase = t2_phase(it);
     if (tid == 0) t2_mbar_expect(mbar_saddr + 8u * (uint32_t)par, 4u * (uint32_t)(kT2CS * kT2Warps * nrw));
     __syncthreads();
-    uint32_t* base = part + ((size_t)(par * kT2CS + q) * NC) * W;
+    uint32_t* base = part + ((size_t)(par * kT2CS + q) * ((NC + 15) & ~15)) * W;
     if (tid < nc4) {
       float s = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < kT2Warps; ++w2) s += red_c[w2 * kT2RedStride + tid];
       st_signed(base + (size_t)p * W + tid, phase, s * u_s[0]);
+      const int NCP = (NC + 15) & ~15;
+      if (p == NC - 1)
+        for (int pp = NC; pp < NCP; ++pp) st_signed(base + (size_t)pp * W + tid, phase, 0.f);
       float tot = 0.f;
       bool timed_out = false;
       int never = 0;
-      for (int pp = 0; pp < NC; pp += 16)
-        tot += t2_poll_sum(base + (size_t)pp * W + tid, 4u * (uint32_t)W, min(16, NC - pp), phase, &never, &timed_out);
+      for (int pp = 0; pp < NCP; pp += 16)
+        tot += t2_poll_sum<16>(base + (size_t)pp * W + tid, phase, &never, &timed_out);
       if (timed_out) atomicMax(&st->fallback, 2);
       v_s[tid] = 1.0f / tot;
     }
@@ -863,7 +875,7 @@ int sinkhorn_tile2d_sync_floor_launch(int64_t I, int64_t J, int iters, void* par
   auto kern = sinkhorn_tile2d_sync_floor_kernel;
   int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
-  const size_t words = (size_t)2 * kT2CS * g.nc * t2_words(g.gs);
+  const size_t words = (size_t)2 * kT2CS * ((g.nc + 15) & ~15) * t2_words(g.gs);
   if (g.nc == 0 || words * 4 > part_bytes) return EG_OK;
   EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));
   EG_CUDA(cudaMemsetAsync(part, 0, words * 4, s));               // sign bit 0 everywhere = "not yet published"
@@ -887,7 +899,7 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
   auto kern = sinkhorn_tile2d_kernel;
   int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
-  const size_t words = (size_t)2 * kT2CS * g.nc * t2_words(g.gs);
+  const size_t words = (size_t)2 * kT2CS * ((g.nc + 15) & ~15) * t2_words(g.gs);
   if (g.nc == 0 || words * 4 > part_bytes) return EG_OK;
   EG_CUDA(cudaMemsetAsync(st, 0, sizeof(PersistState), s));      // the probe may have used it
   EG_CUDA(cudaMemsetAsync(part, 0, words * 4, s));               // sign bit 0 everywhere = "not yet published"
