@@ -91,7 +91,7 @@ class _Aggregate(torch.autograd.Function):
         dH = None
         if need_h:
             if getattr(ctx.adjacency, "sharded", False):
-                dS = ctx.adjacency.gather(dS)
+                dS = ctx.adjacency.gather(dS, transposed=True)
             dH, _ = ops.spmm(ctx.adjacency.csr_t, dS, _lib.ACT_IDENTITY)
         return dH, d_gate, d_xres, None, None
 

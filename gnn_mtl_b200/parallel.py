@@ -7,8 +7,9 @@ NVLink/NVSwitch) for the exchanges the path really has.
     the [G, J] partial log-sum-exps are all-gathered and combined (one 4·J-byte
     exchange per sweep).  Eval: diagonal all-gather + one int32 sum of column
     rank counts.
-  * SpMM: 1-D row partition of A (and of Aᵀ for the backward); feature rows are
-    all-gathered before each aggregation.  Only worth it for graphs beyond one GPU.
+  * SpMM: 1-D row partition of A (and of Aᵀ for the backward); before each aggregation a rank fetches the
+    feature rows its block references (needed-rows exchange, one all-to-all with uneven splits — HaloPlan), or,
+    as the plain variant, all rows (all-gather).  Only worth it for graphs beyond one GPU.
   * Weights are replicated; `allreduce_grads` averages their gradients.
 
 The reference has no distributed code at all (single process), so
@@ -320,13 +321,87 @@ def generate_pairs_sharded(outputs, data, bsz, group=None, argmins_fn=None):
 
 # --------------------------------------------------------------------------- SpMM
 
+class HaloPlan:
+    """Needed-rows ("halo") exchange plan of one row block of a CSR matrix.
+
+    The all-gather moves every feature row to every rank; a rank only reads the rows its own block of A references
+    (on the 10M-node power-law graph of BASELINE.json config 4 at 8 ranks: under half of the remote ones).  The plan is
+    built once per adjacency: the sorted distinct REMOTE column ids of the block, grouped by owner rank (block
+    partition), are sent to their owners (all-to-all of counts, then of indices); every aggregation then is
+        pack = H_local[send_idx]  ->  all_to_all_single with uneven splits into the tail of the operand buffer
+        [ H_local | rows received from rank 0, 1, ... ]  ->  SpMM on the block with its columns REMAPPED into that buffer
+    (own columns: col - r0; remote columns: n_local + position in the sorted need list).  Own rows never travel and are
+    never packed.  The remap is monotone within a row only per segment (own / remote), so the summation order inside a
+    row can differ from the all-gather route's: results agree to fp32 rounding, not bit for bit, unless the block has
+    no own columns."""
+
+    def __init__(self, csr_block, n_total, group=None):
+        from .adjacency import _Csr
+        self.group = group
+        rank, size = world(group)
+        dev = csr_block.col.device
+        per = -(-n_total // size)
+        r0, r1 = shard_range(n_total, rank, size)
+        self.n_local = r1 - r0
+        cols = csr_block.col.to(torch.int64)
+        remote = (cols < r0) | (cols >= r1)
+        need = torch.unique(cols[remote])                           # sorted -> grouped by owner rank, in rank order
+        owner = torch.div(need, per, rounding_mode="floor")
+        counts_in = torch.bincount(owner, minlength=size).to(torch.int64)       # rows I receive from every rank
+        counts_out = torch.empty_like(counts_in)
+        if size > 1:
+            dist.all_to_all_single(counts_out, counts_in, group=group)
+        else:
+            counts_out.copy_(counts_in)
+        self.in_splits = [int(v) for v in counts_in.tolist()]       # receive sizes (rows)
+        self.out_splits = [int(v) for v in counts_out.tolist()]     # send sizes (rows)
+        wanted = torch.empty(sum(self.out_splits), dtype=torch.int64, device=dev)
+        if size > 1:
+            dist.all_to_all_single(wanted, need, output_split_sizes=self.out_splits, input_split_sizes=self.in_splits,
+                                   group=group)
+        self.send_idx = (wanted - r0).contiguous()                  # my local rows, in the order the peers expect them
+        self.n_need = int(need.numel())                             # remote rows this rank reads
+        self.n_remote_total = n_total - self.n_local
+        new_col = torch.where(remote, self.n_local + torch.searchsorted(need, cols), cols - r0)
+        # the kernels read the (col, val) pairs of a row in storage order: keep every row sorted by the new column id
+        # is not required for correctness, only the order of summation changes
+        self.csr = _Csr(csr_block.n_rows, max(self.n_local + self.n_need, 1), csr_block.rowptr,
+                        new_col.to(torch.int32).contiguous(), csr_block.val, csr_block.threshold)
+
+    def exchange(self, local_rows):
+        """[rows of this rank, d] -> [n_local + n_need, d]: own rows, then the remote rows this block references."""
+        rank, size = world(self.group)
+        out = torch.empty((max(self.n_local + self.n_need, 1),) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype,
+                          device=local_rows.device)
+        if self.n_local + self.n_need == 0:
+            out.zero_()
+        out[:self.n_local].copy_(local_rows)
+        if size > 1:
+            pack = local_rows.index_select(0, self.send_idx)
+            dist.all_to_all_single(out[self.n_local:self.n_local + self.n_need], pack,
+                                   output_split_sizes=self.in_splits, input_split_sizes=self.out_splits, group=self.group)
+        return out
+
+    def remote_fraction(self):
+        """Largest fraction, over ranks, of the remote rows a rank has to fetch (1.0 = as many as an all-gather)."""
+        rank, size = world(self.group)
+        f = torch.tensor([self.n_need / max(self.n_remote_total, 1)], dtype=torch.float64, device=self.csr.col.device)
+        if size > 1:
+            dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
+        return float(f[0])
+
+
 class ShardedAdjacency:
-    """Row block [r0, r1) of A and of Aᵀ (kernel-format CSR, full column range).
-    `gather` all-gathers the feature rows every aggregation needs."""
+    """Row block [r0, r1) of A and of Aᵀ (kernel-format CSR).
+    ``halo=False``: full column range; `gather` all-gathers every feature row before an aggregation.
+    ``halo=True``: columns remapped into [own rows | fetched rows]; `gather` exchanges only the remote rows the block
+    references (HaloPlan) — a fraction of the bytes over NVLink where the graph is sparse enough.
+    ``halo="auto"``: the plan is built, and used iff every rank fetches under 60 % of its remote rows (at 2 ranks the
+    power-law benchmark graph needs 70 % of them and the all-gather wins; at 8 ranks under half)."""
 
     sharded = True
 
-    def __init__(self, full, group=None):
+    def __init__(self, full, group=None, halo=False):
         from .adjacency import _Csr
         self.group = group
         self.rank, self.size = world(group)
@@ -335,13 +410,27 @@ class ShardedAdjacency:
         self.csr = self._slice(full.csr, _Csr)
         self.csr_t = self._slice(full.csr_t, _Csr)
         self.device = full.device
+        self.halo = bool(halo)
+        self.remote_fraction = None
+        if self.halo:
+            self.plan = HaloPlan(self.csr, self.n, group)
+            self.plan_t = HaloPlan(self.csr_t, self.n, group)
+            self.remote_fraction = max(self.plan.remote_fraction(), self.plan_t.remote_fraction())
+            if halo == "auto" and self.remote_fraction >= 0.6:
+                self.halo = False
+                del self.plan, self.plan_t
+            else:
+                self.csr, self.csr_t = self.plan.csr, self.plan_t.csr
 
     def _slice(self, c, _Csr):
         e0, e1 = int(c.rowptr[self.r0]), int(c.rowptr[self.r1])
         rowptr = (c.rowptr[self.r0:self.r1 + 1] - e0).contiguous()
         return _Csr(self.r1 - self.r0, c.n_cols, rowptr, c.col[e0:e1].clone(), c.val[e0:e1].clone(), c.threshold)
 
-    def gather(self, local_rows):
+    def gather(self, local_rows, transposed=False):
+        """The operand the SpMM on `csr` (or, transposed, `csr_t`) reads: all rows, or this rank's halo."""
+        if self.halo:
+            return (self.plan_t if transposed else self.plan).exchange(local_rows)
         return all_gather_rows(local_rows, self.n, self.group)
 
     def local(self, full_rows):
@@ -350,5 +439,7 @@ class ShardedAdjacency:
     def aggregate_overlapped(self, local_rows, transposed=False, n_chunks=4):
         """(A or Aᵀ)[my rows] · H with the feature all-gather pipelined against the SpMM over column chunks."""
         from . import ops
+        if self.halo:
+            raise ValueError("aggregate_overlapped is the all-gather route; build the adjacency with halo=False")
         csr = self.csr_t if transposed else self.csr
         return gather_apply_overlapped(local_rows, self.n, lambda g: ops.spmm(csr, g)[0], n_chunks, self.group)

@@ -60,6 +60,14 @@ def main():
     assert float((y_loc - y_full[sh.r0:sh.r1]).abs().max()) < 1e-5
     assert float((xl.grad - xf.grad[sh.r0:sh.r1]).abs().max()) < 1e-5
     assert float((gWl - gW).abs().max() / gW.abs().max()) < 1e-4
+    # ---- (a') the same layer over the needed-rows exchange (HaloPlan): the all-gather route's result to fp32 rounding ----
+    shh = par.ShardedAdjacency(full, halo=True)
+    layer.zero_grad()
+    xh = x[shh.r0:shh.r1].clone().requires_grad_(True)
+    y_h, _ = layer((xh, shh))
+    (y_h * seed[shh.r0:shh.r1]).sum().backward()
+    assert float((y_h - y_loc).abs().max()) < 1e-5 and float((xh.grad - xl.grad).abs().max()) < 1e-5
+    assert shh.plan.n_need <= full.n - (shh.r1 - shh.r0)
     # ---- (d) all-gather pipelined against the SpMM over column chunks: bit-identical to gather-then-SpMM ----
     from gnn_mtl_b200 import ops
     Hl = x[sh.r0:sh.r1].contiguous()

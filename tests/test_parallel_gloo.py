@@ -145,6 +145,51 @@ def _w_sharded_adjacency(rank, world):
         assert int(c.seg_begin.min()) >= 0 and int(c.seg_end.max()) <= c.nnz
 
 
+def _w_halo_exchange(rank, world):
+    """Needed-rows exchange: the remapped block times the received rows == the block of the full product, bit for
+    bit (the remap is monotone, so the summation order inside a row does not change); only referenced rows travel."""
+    import scipy.sparse as sp
+    from oracle import ea_oracle as orc
+    from gnn_mtl_b200 import parallel as par
+    from gnn_mtl_b200.adjacency import _Csr
+    rng = np.random.default_rng(2)
+    for n, nt in ((53, 120), (7, 3), (200, 150)):
+        h, t = rng.integers(0, n, nt), rng.integers(0, max(n // 2, 1), nt)     # unsymmetric reference pattern
+        A = sp.csr_matrix((rng.standard_normal(nt).astype(np.float32), (h, t)), shape=(n, n))
+        A.sum_duplicates(); A.sort_indices()
+        At = A.T.tocsr(); At.sort_indices()
+
+        class _Full:
+            pass
+        full = _Full()
+        full.n, full.device = n, torch.device("cpu")
+        mk = lambda M: _Csr(n, n, torch.from_numpy(M.indptr.astype(np.int32)), torch.from_numpy(M.indices.astype(np.int32)),
+                            torch.from_numpy(M.data.astype(np.float32)), threshold=4)
+        full.csr, full.csr_t = mk(A), mk(At)
+        sh = par.ShardedAdjacency(full, halo=True)
+        plain = par.ShardedAdjacency(full)
+        H = rng.standard_normal((n, 5)).astype(np.float32)
+        Hl = torch.from_numpy(H[sh.r0:sh.r1])
+        for transposed, M in ((False, A), (True, At)):
+            plan = sh.plan_t if transposed else sh.plan
+            buf = sh.gather(Hl, transposed=transposed)
+            c = sh.csr_t if transposed else sh.csr
+            nl = sh.r1 - sh.r0
+            assert buf.shape[0] == max(nl + plan.n_need, 1) and c.n_cols == buf.shape[0]
+            pc = plain.csr_t if transposed else plain.csr
+            cols = pc.col.numpy()
+            need = np.unique(cols[(cols < sh.r0) | (cols >= sh.r1)])
+            assert plan.n_need == need.size                                        # only referenced REMOTE rows travel
+            assert np.array_equal(buf.numpy()[:nl], H[sh.r0:sh.r1])                 # own rows in place
+            assert np.array_equal(buf.numpy()[nl:nl + plan.n_need], H[need])
+            loc = sp.csr_matrix((c.val.numpy(), c.col.numpy(), c.rowptr.numpy()), shape=(c.n_rows, c.n_cols))
+            assert np.allclose(loc @ buf.numpy(), (M @ H)[sh.r0:sh.r1], atol=1e-5)
+        assert 0.0 <= sh.remote_fraction <= 1.0
+        auto = par.ShardedAdjacency(full, halo="auto")
+        assert auto.halo == (auto.remote_fraction < 0.6)
+        assert auto.csr.n_cols == (sh.csr.n_cols if auto.halo else n)
+
+
 def _w_overlapped_gather(rank, world):
     """Column-chunked gather + column-wise operator == unchunked call, bit for bit; chunk bounds aligned."""
     from gnn_mtl_b200 import parallel as par
@@ -223,6 +268,7 @@ def _w_overlapped_grad_sync(rank, world):
 
 
 @pytest.mark.parametrize("worker", [_w_sinkhorn, _w_gather_and_grads, _w_rank_merge, _w_sharded_adjacency,
-                                    _w_overlapped_gather, _w_sharded_neg_and_pairs, _w_overlapped_grad_sync])
+                                    _w_overlapped_gather, _w_sharded_neg_and_pairs, _w_overlapped_grad_sync,
+                                    _w_halo_exchange])
 def test_world2_gloo(worker):
     _run(worker, 2)

@@ -15,6 +15,9 @@ h, t = make_powerlaw_graph(n, deg, seed=1)
 full = DeviceAdjacency.from_heads_tails(n, torch.from_numpy(h).to(dev), torch.from_numpy(t).to(dev))
 nnz = full.nnz
 sh = par.ShardedAdjacency(full) if world > 1 else None
+shh = par.ShardedAdjacency(full, halo=True) if world > 1 else None
+if shh and rank == 0:
+    print("halo: rank 0 fetches %d of %d remote rows; max fraction over ranks %.3f" % (shh.plan.n_need, shh.plan.n_remote_total, shh.remote_fraction), flush=True)
 del h, t
 res = []
 for d in (128, 300):
@@ -29,10 +32,17 @@ for d in (128, 300):
         return sh.gather(H_local) if sh else H_local
     def fwd_overlap():
         return sh.aggregate_overlapped(H_local, n_chunks=4) if sh else fwd()
+    def fwd_halo():
+        return ops.spmm(shh.csr, shh.gather(H_local))[0] if shh else fwd()
+    def halo_exchange_only():
+        return shh.gather(H_local) if shh else H_local
+    if shh:
+        assert float((fwd_halo() - fwd()).abs().max()) < 1e-4     # needed-rows exchange: same result to fp32 rounding
     if sh:
         assert torch.equal(fwd_overlap(), fwd())          # column chunks do not change a single bit
     out = {}
-    for name, f in (("fwd", fwd), ("bwd", bwd), ("allgather", gather_only), ("fwd_overlap", fwd_overlap)):
+    for name, f in (("fwd", fwd), ("bwd", bwd), ("allgather", gather_only), ("fwd_overlap", fwd_overlap),
+                    ("fwd_halo", fwd_halo), ("halo_exchange", halo_exchange_only)):
         for _ in range(2): f()
         torch.cuda.synchronize()
         if world > 1: dist.barrier()
@@ -45,7 +55,7 @@ for d in (128, 300):
         out[name] = float(ms[0])
     byt = nnz * 8 + (n + 1) * 4 + nnz * d * 4 + n * d * 4
     res.append({"d": d, "fwd_ms": out["fwd"], "bwd_ms": out["bwd"], "allgather_ms": out["allgather"],
-                "fwd_overlap_ms": out["fwd_overlap"], "fwd_overlap_gbs_aggregate": byt / out["fwd_overlap"] / 1e6,
+                "fwd_overlap_ms": out["fwd_overlap"], "fwd_halo_ms": out["fwd_halo"], "halo_exchange_ms": out["halo_exchange"], "fwd_overlap_gbs_aggregate": byt / out["fwd_overlap"] / 1e6,
                 "fwd_gbs_aggregate": byt / out["fwd"] / 1e6, "bwd_gbs_aggregate": byt / out["bwd"] / 1e6,
                 "spmm_only_gbs_aggregate": byt / max(out["fwd"] - out["allgather"], 1e-6) / 1e6})
 if rank == 0:
