@@ -141,9 +141,9 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2 * BN * 8);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* tfull = bars + 2 * STAGES;   // [3]  (MODE 3 rotates three accumulator buffers, the others two)
+  uint64_t* tempty = bars + 2 * STAGES + 3;   // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.x * BM;
@@ -165,7 +165,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation is a warp-wide instruction; this warp also frees it
@@ -217,10 +217,10 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          if (MODE == 3) {                                 // a fresh accumulator per k-block, buffers alternate
-            buf = (int)(chain & 1u);
-            tmem_d = tmem_base + (uint32_t)(buf * BN);
-            mbar_wait(&tempty[buf], ((chain >> 1) & 1u) ^ 1u);
+          if (MODE == 3) {                                 // a fresh accumulator per k-block, three buffers rotate
+            buf = (int)(chain % 3u);                       // (3 x 160 TMEM columns: the MMAs run two chains ahead
+            tmem_d = tmem_base + (uint32_t)(buf * kFlushBN);   //  of the fold, which hides the commit -> wake-up hand-off)
+            mbar_wait(&tempty[buf], ((chain / 3u) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           mbar_wait(&full[s], ph);
@@ -278,17 +278,25 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         for (int c = 0; c < kFlushBN; ++c) accf[c] = 0.f;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const uint32_t chain = (uint32_t)t * (uint32_t)p.k_blocks + (uint32_t)kb;
-          const int cb = (int)(chain & 1u);
-          mbar_wait(&tfull[cb], (chain >> 1) & 1u);
+          const int cb = (int)(chain % 3u);
+          mbar_wait(&tfull[cb], (chain / 3u) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * BN);
+          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * kFlushBN);
 #pragma unroll
-          for (int c0 = 0; c0 < kFlushBN; c0 += 32) {
+          for (int c0 = 0; c0 < kFlushBN; c0 += 64) {        // two loads in flight per wait
             if (c0 < bn) {                                   // CTA-uniform
-              float dot[32];
-              tmem_ld32(ta + (uint32_t)c0, dot);
+              uint32_t r0[32], r1[32];
+              const bool two = (c0 + 32 < kFlushBN) && (c0 + 32 < bn);
+              tmem_ld32_issue(ta + (uint32_t)c0, r0);
+              if (two) tmem_ld32_issue(ta + (uint32_t)(c0 + 32), r1);
+              tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 32; ++c) accf[c0 + c] += dot[c];
+              for (int c = 0; c < 32; ++c) accf[c0 + c] += __uint_as_float(r0[c]);
+              if (two) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c0 + 32 + c < kFlushBN) accf[c0 + 32 + c] += __uint_as_float(r1[c]);
+              }
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

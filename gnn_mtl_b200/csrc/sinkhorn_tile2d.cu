@@ -239,6 +239,9 @@ __host__ __device__ inline T2Smem t2_carve(int nrw, int gs) {
   return s;
 }
 
+// TIMING = true (EG_PERSIST_TIMING set): CTA 0 accumulates per-phase globaltimer deltas; the shipping instantiation has
+// none of that code.
+template <bool TIMING>
 __global__ void __cluster_dims__(kT2CS, 1, 1) __launch_bounds__(kT2Threads, 1)
 sinkhorn_tile2d_kernel(const T2Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw_t2[];
@@ -349,7 +352,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
   double err = 1.0;
   bool stop_hit = false;
   int pending_cpt = -1;                          // sweep whose marginal-error check is decided one exchange later
-  const bool timer = (blockIdx.x == 0 && tid == 0);
+  const bool timer = TIMING && (blockIdx.x == 0 && tid == 0);
   const uint32_t rowpart_saddr = (uint32_t)__cvta_generic_to_shared(rowpart);
   const uint32_t ctrl_saddr = (uint32_t)__cvta_generic_to_shared(ctrl_in);
 
@@ -384,11 +387,14 @@ sinkhorn_tile2d_kernel(const T2Params P) {
     return s;
   };
 
+  // sweeps until the next marginal-error check: the first sweep >= start_iter with (cpt - 1) % 10 == 0 and cpt >= 1
+  int until_check = (P.start_iter <= 1) ? (1 - P.start_iter) : ((10 - (P.start_iter - 1) % 10) % 10);
   for (cpt = P.start_iter; cpt < P.max_iter; ++cpt) {
     const int par = cpt & 1;
-    const bool check = (cpt >= 1) && ((cpt - 1) % 10 == 0);
+    const bool check = (until_check == 0);         // sweeps 1, 11, 21, ... (utils/ot_loss.py:63: cpt % 10 == 0 after the increment)
+    until_check = check ? 9 : until_check - 1;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
-    if (timer) t0 = gtime();
+    if (TIMING && timer) t0 = gtime();
     // this sweep's inbox: 8 peers x (16 warps x nrw rows) floats, + 8 error shares on a checking sweep
     if (tid == 0) t2_mbar_expect(mbar_saddr + 8u * (uint32_t)par, 4u * (uint32_t)(kT2CS * kT2Warps * nrw + (check ? kT2CS : 0)));
     // ---- C: column partials of my tile (thread: 3 column groups x the warp's rows), packed FMAs ----------------
@@ -404,22 +410,24 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
         for (int g = 0; g < kT2QG; ++g) fma4s(acc[g], kreg[r][g], ur[r]);
       const float* uw = u_s + wrow0 + kT2RRW;
-#pragma unroll 1
-      for (int sp = 0; sp < SRP; ++sp) {
-        float k[2 * kT2TmemColsPerRow];
-        tmem_ld_row_pair(tmem_w + (uint32_t)(sp * 2 * kT2TmemColsPerRow), k);
-        const float ua = uw[2 * sp], ub = uw[2 * sp + 1];      // (finite even for the padding row; its entries are 0)
 #pragma unroll
-        for (int g = 0; g < kT2QG; ++g) {
-          fma4s(acc[g], make_float4(k[4 * g], k[4 * g + 1], k[4 * g + 2], k[4 * g + 3]), ua);
-          fma4s(acc[g], make_float4(k[12 + 4 * g], k[13 + 4 * g], k[14 + 4 * g], k[15 + 4 * g]), ub);
+      for (int sp = 0; sp < (kT2MaxRowsPerWarp - kT2RRW) / 2; ++sp) {
+        if (sp < SRP) {                          // warp-uniform; unrolled so the TMEM addresses are immediates
+          float k[2 * kT2TmemColsPerRow];
+          tmem_ld_row_pair(tmem_w + (uint32_t)(sp * 2 * kT2TmemColsPerRow), k);
+          const float ua = uw[2 * sp], ub = uw[2 * sp + 1];    // (finite even for the padding row; its entries are 0)
+#pragma unroll
+          for (int g = 0; g < kT2QG; ++g) {
+            fma4s(acc[g], make_float4(k[4 * g], k[4 * g + 1], k[4 * g + 2], k[4 * g + 3]), ua);
+            fma4s(acc[g], make_float4(k[12 + 4 * g], k[13 + 4 * g], k[14 + 4 * g], k[15 + 4 * g]), ub);
+          }
         }
       }
 #pragma unroll
       for (int g = 0; g < kT2QG; ++g)
-        if (lg[g] < Gs)
+        if (lg[g] < Gs)                          // (dead groups: their tile entries are zero, so is the sum)
           reinterpret_cast<float4*>(red_c)[warp * (kT2RedStride / 4) + lg[g]] =
-              gok[g] ? make_float4(acc[g].lo.x, acc[g].lo.y, acc[g].hi.x, acc[g].hi.y) : make_float4(0.f, 0.f, 0.f, 0.f);
+              make_float4(acc[g].lo.x, acc[g].lo.y, acc[g].hi.x, acc[g].hi.y);
     }
     __syncthreads();
     float mine = 0.f;
@@ -427,10 +435,10 @@ sinkhorn_tile2d_kernel(const T2Params P) {
 #pragma unroll
       for (int w2 = 0; w2 < kT2Warps; ++w2) mine += red_c[w2 * kT2RedStride + tid];
     }
-    if (timer) t1 = gtime();
+    if (TIMING && timer) t1 = gtime();
     // ---- all clusters' partials of MY columns -> v on my slice (every CTA of slice q computes the same bits) ----
     const float s = exchange(cpt, mine, true);
-    if (timer) t2 = gtime();
+    if (TIMING && timer) t2 = gtime();
     if (check) {   // back-up of the iterate the check refers to (before sweep cpt touches it), as full potentials
       for (int r = tid; r < rb_pad; r += kT2Threads) bak_f[r] = LU_s[r] + log2((double)u_s[r]);
     }
@@ -462,7 +470,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       }
     }
     __syncthreads();
-    if (timer) t3 = gtime();
+    if (TIMING && timer) t3 = gtime();
     if (pending_cpt >= 0) {                      // the check issued one sweep ago: same word in every CTA
       err = sqrt((double)ctrl_f[1]);
       const bool stop = !(err > P.stop_thr);
@@ -529,7 +537,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
         }
       }
       const float tot = warp_transpose_sum16(dots, lane);
-      if (timer) t4 = gtime();
+      if (TIMING && timer) t4 = gtime();
       const int r = lane & 15;
       const uint32_t inbox_bar = mbar_saddr + 8u * (uint32_t)par;
       if (r < nrw) {
@@ -610,7 +618,7 @@ sinkhorn_tile2d_kernel(const T2Params P) {
       __syncthreads();
     }
     sweeps = cpt + 1;
-    if (timer) {
+    if (TIMING && timer) {
       t5 = gtime();
       st->t_phase[0] += t1 - t0; st->t_phase[1] += t2 - t1; st->t_phase[2] += t3 - t2;
       st->t_phase[3] += t4 - t3; st->t_phase[4] += t5 - t4;
@@ -896,7 +904,8 @@ int sinkhorn_tile2d_launch(const float* M, int64_t I, int64_t J, int64_t ld, dou
   T2Geometry g;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attrs[2];
-  auto kern = sinkhorn_tile2d_kernel;
+  const bool timing = getenv("EG_PERSIST_TIMING") != nullptr;
+  auto kern = timing ? sinkhorn_tile2d_kernel<true> : sinkhorn_tile2d_kernel<false>;
   int rc = t2_geometry(kern, I, J, s, st, &g, &cfg, attrs);
   if (rc) return rc;
   const size_t words = (size_t)2 * kT2CS * ((g.nc + 15) & ~15) * t2_words(g.gs);
