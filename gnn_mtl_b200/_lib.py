@@ -64,6 +64,8 @@ SIGNATURES = {
                                     _i64, _vp]),
     "eg_gemm_nt_3xtf32_chained": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp,
                                     _i64, _vp]),
+    "eg_gemm_nt_3xtf32_raw": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp,
+                                        _i64, _i64, _vp, _i64, _vp]),
     "eg_margin_loss_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp]),
     "eg_margin_loss_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),
     "eg_gemm_tn_3xtf32_workspace_bytes": (_sz, [_i64, _i32, _i32]),

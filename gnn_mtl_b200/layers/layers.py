@@ -177,12 +177,13 @@ class _DenseProducts(torch.autograd.Function):
             d_hidden = torch.zeros(x.shape[0], weight.shape[0], device=x.device)
         d_hidden = d_hidden.contiguous()
         use_tc_dw = USE_TCGEN05_DW and ctx.needs_input_grad[1] and weight.shape[0] % 4 == 0 and x.shape[1] % 4 == 0
-        dh_split = ops.split_tf32(d_hidden, ops._pad16(d_hidden.shape[1])) if (use_tc_dw or ctx.needs_input_grad[0]) else None
+        dh_split = (ops.split_tf32(d_hidden, ops._pad16(d_hidden.shape[1]))
+                    if (use_tc_dw or (ctx.needs_input_grad[0] and not (ctx.has_gate and d_gate is not None))) else None)
         if ctx.needs_input_grad[0]:
             if ctx.has_gate and d_gate is not None:
-                dg = d_gate.contiguous()
-                dx = ops.gemm_nt([d_hidden, dg], torch.cat([weight.t(), gate_w], 1),
-                                 a_splits=[dh_split, ops.split_tf32(dg, ops._pad16(dg.shape[1]))])
+                # raw-operand kernel (hi/lo split inside the kernel): d_gate is used here only, so its split pass
+                # (a launch + 0.7 GB of HBM traffic) disappears; same bits as the split-operand product
+                dx = ops.gemm_nt_raw([d_hidden, d_gate.contiguous()], torch.cat([weight.t(), gate_w], 1))
             else:
                 dx = ops.gemm_nt([d_hidden], weight.t().contiguous(), a_splits=[dh_split])
         if ctx.needs_input_grad[1]:

@@ -409,6 +409,45 @@ def gemm_tn(a_split, m, b_split, n):
     return out
 
 
+def gemm_nt_raw(A_parts, B, bias=None, n1=None, addend=None):
+    """C = [A1 | A2] · Bᵀ + bias (+ addend) with RAW fp32 A operands: their hi/lo split happens inside the kernel
+    (eg_gemm_nt_3xtf32_raw) — no eg_split_tf32 pass over A, a deeper TMA ring.  Bit-identical to ``gemm_nt``.
+    A_parts: one or two [m, k_i] fp32 CUDA tensors with k_i % 4 == 0; B: [n, sum k_i]; addend: [m, n] (n1 == n)."""
+    A_parts = [_f32c(a) for a in A_parts]
+    if not 1 <= len(A_parts) <= 2:
+        raise ValueError("gemm_nt_raw takes one or two A operands")
+    m = A_parts[0].shape[0]
+    ks = [a.shape[1] for a in A_parts]
+    B = _f32c(B)
+    n = B.shape[0]
+    if B.shape[1] != sum(ks):
+        raise ValueError("gemm_nt_raw: B has %d columns, A parts have %s" % (B.shape[1], ks))
+    n1 = n if n1 is None else n1
+    dev = B.device
+    if len(ks) == 1 and ks[0] % 16 == 0:
+        Bp = B
+    else:
+        Bp = torch.zeros(n, sum(_pad16(k) for k in ks), dtype=torch.float32, device=dev)
+        src = dst = 0
+        for k in ks:
+            Bp[:, dst:dst + k] = B[:, src:src + k]
+            src += k
+            dst += _pad16(k)
+    b_hi, b_lo = split_tf32(Bp, Bp.shape[1])
+    out1 = torch.empty(m, n1, dtype=torch.float32, device=dev)
+    out2 = torch.empty(m, n - n1, dtype=torch.float32, device=dev) if n1 < n else None
+    bias = _f32c(bias) if bias is not None else None
+    addend = _f32c(addend) if addend is not None else None
+    a2 = A_parts[1] if len(A_parts) == 2 else None
+    with torch.cuda.device(dev):
+        check(lib.eg_gemm_nt_3xtf32_raw(ptr(A_parts[0]), ks[0], ks[0], ptr(a2), ks[1] if a2 is not None else 0,
+                                        ks[1] if a2 is not None else 0, m, ptr(b_hi), ptr(b_lo), Bp.shape[1], n, ptr(bias),
+                                        ptr(addend), n if addend is not None else 0,
+                                        ptr(out1), n1, n1, ptr(out2), (n - n1) if out2 is not None else 0, stream()),
+              "eg_gemm_nt_3xtf32_raw")
+    return (out1, out2) if out2 is not None else out1
+
+
 def gemm_nt(A_parts, B, bias=None, n1=None, a_splits=None, return_splits=False, chained=False):
     """C = [A1 | A2 ...] · Bᵀ + bias with fp32 accuracy (3xTF32 on tcgen05).
     ``chained=True``: short accumulation chains folded in fp32 registers (eg_gemm_nt_3xtf32_chained): ~3e-7 relative

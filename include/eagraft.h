@@ -260,6 +260,17 @@ int eg_gemm_nt_3xtf32(const float* A1_hi, const float* A1_lo, int k1_pad,
                       const float* A2_hi, const float* A2_lo, int k2_pad, int64_t m,
                       const float* B_hi, const float* B_lo, int64_t n, const float* bias,
                       float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
+/* Same product with the A operands RAW (fp32): their hi/lo split is done inside the kernel (converter warps between
+ * the TMA ring and the MMAs write the pair into tensor memory, from where tcgen05.mma reads its A operand), so the
+ * streamed operand costs 8 KB instead of 16 KB per k-block, its ring is ten stages deep instead of four, and no
+ * eg_split_tf32 pass over A is needed.  A1 [m, k1] and A2 [m, k2] row-major with row strides lda1 / lda2 (multiples
+ * of 4, no K padding needed); B_hi / B_lo [n, ldb]: eg_split_tf32 of the weights with the two K parts back to back,
+ * each zero-padded to a multiple of 16 columns; addend (nullable, requires n1 == n): [m, ld_add] added to the result.
+ * Bit-identical to eg_split_tf32 + eg_gemm_nt_3xtf32. */
+int eg_gemm_nt_3xtf32_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t lda2, int k2, int64_t m,
+                          const float* B_hi, const float* B_lo, int64_t ldb, int64_t n, const float* bias,
+                          const float* addend, int64_t ld_add,
+                          float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, eg_stream_t stream);
 /* Same product with SHORT ACCUMULATION CHAINS (a fresh tensor-memory accumulator every 6 MMAs, folded into fp32
  * registers): ~3e-7 relative instead of ~2e-6, i.e. the accuracy of an fp32 SIMT product.  For the products
  * that feed a ReLU through the aggregation (layers/layers.py:32-38, 61-64), where a 2e-6 error flips the sign of

@@ -570,6 +570,27 @@ def test_gemm_nt_chained_is_fp32_accurate(m, k, n, n1, dev):
     assert float((got.double() - ref).mean().abs()) < 3e-7 * float(ref.abs().mean()) + 1e-9
 
 
+@pytest.mark.parametrize("m,k,k2,n,n1", [(1, 16, 0, 4, 4), (130, 52, 36, 340, 20), (4099, 300, 300, 300, 300), (777, 36, 0, 260, 128),
+                                         (128 * 149 + 5, 300, 0, 600, 300)])
+def test_gemm_nt_raw_operands_bit_identical(m, k, k2, n, n1, dev):
+    """eg_gemm_nt_3xtf32_raw (hi/lo split inside the kernel; layers/layers.py:61,69 products and their dx) gives the
+    bits of eg_split_tf32 + eg_gemm_nt_3xtf32: ragged K (no padding of the A operands), two A operands, two outputs,
+    and the fused addend."""
+    from gnn_mtl_b200 import ops
+    torch.manual_seed(m + k)
+    parts = [torch.randn(m, k, device=dev)] + ([torch.randn(m, k2, device=dev)] if k2 else [])
+    B = torch.randn(n, k + k2, device=dev) * 0.1
+    bias = torch.randn(n, device=dev)
+    want = ops.gemm_nt(parts, B, bias, n1=n1)
+    got = ops.gemm_nt_raw(parts, B, bias, n1=n1)
+    cat = lambda r: torch.cat(r, 1) if isinstance(r, tuple) else r
+    assert torch.equal(cat(got), cat(want))
+    ref = torch.cat(parts, 1).double() @ B.double().t() + bias.double()
+    assert relerr(cat(got), ref) < 1e-5
+    add = torch.randn(m, n, device=dev)
+    assert torch.equal(ops.gemm_nt_raw(parts, B, bias, addend=add), cat(ops.gemm_nt(parts, B, bias)) + add)
+
+
 def test_margin_loss_golden_and_scale(golden_dir, dev):
     """Fused gather + L1 + hinge loss (models/models_ea.py:103-123): value and gradient."""
     from oracle import ea_oracle as orc
