@@ -24,6 +24,7 @@ int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelin
 int g_tune_spmm_slab = 0;   // eg_debug_set(14, v): v in {32, 64}: walk the feature columns in slabs of v float4 (one launch
                             // per slab, rows inner) so that a slab of H stays L2-resident; 0: as wide as the kernel allows
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
+int g_tune_spmm_bulk = 0;   // eg_debug_set(16, 1): neighbour rows fetched by cp.async.bulk into shared memory (spmm_bulk_kernel)
 
 struct Epilogue {
   const float* gate_pre;
@@ -186,6 +187,126 @@ spmm_vec_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
 #pragma unroll
     for (int p = 0; p < VPL; ++p) {
       int k = lane + 32 * p;
+      if (k < d4_local) dst[k] = acc[p];
+    }
+  }
+}
+
+// ---- bulk-copy variant: the feature rows of a CSR row travel as cp.async.bulk copies into shared memory ---------
+// The register-gather kernel above keeps 2 neighbour rows (3 KB) in flight per warp and ~25 warps per SM: 75 KB per SM
+// against a ~1.7 us gather latency = the 6 TB/s of L2 -> SM traffic the captures show (Little's law, not a bandwidth
+// limit).  Here lane 0 of a warp hands the copy engine one 16-byte-aligned row (d4 * 16 bytes) per neighbour, up to
+// SLOTS rows ahead — for the benchmark graph's ~11 neighbours per row the WHOLE row is in flight at once — each landing
+// in a shared-memory slot guarded by its own mbarrier (complete_tx); the warp then streams the slots through the FMAs
+// in CSR order (same summation order, same bits).  Bytes in flight are bounded by shared memory (SLOTS x 1.2 KB per
+// warp), not by registers.
+__device__ __forceinline__ void bulk_row_to_smem(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst), b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bar_wait_parity(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(b), "r"(parity) : "memory");
+}
+
+template <int VPL, int SLOTS>
+__device__ __forceinline__ void gather_rows_bulk(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                                 const float4* __restrict__ Hc, int d4, int d4_local, int b, int e,
+                                                 int lane, unsigned char* slots, uint32_t slot_bytes, uint64_t* bars,
+                                                 uint32_t& ph, float4 (&acc)[VPL]) {
+  for (int base = b; base < e; base += 32) {
+    const int idx = base + lane;
+    int my_col = 0;
+    float my_val = 0.f;
+    if (idx < e) {
+      my_col = ld_stream_i32(col + idx);
+      my_val = ld_stream_f32(val + idx);
+    }
+    const int cnt = min(32, e - base);
+    // up to SLOTS rows of this chunk go out at once
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {
+      const int c = __shfl_sync(0xffffffffu, my_col, t);
+      if (t < cnt && lane == 0) bulk_row_to_smem(slots + t * slot_bytes, Hc + (int64_t)c * d4, slot_bytes, bars + t);
+    }
+    int s = 0;
+    for (int t = 0; t < cnt; ++t) {
+      bar_wait_parity(bars + s, (ph >> s) & 1u);
+      ph ^= 1u << s;
+      const float v = __shfl_sync(0xffffffffu, my_val, t);
+      const float4* row = reinterpret_cast<const float4*>(slots + s * slot_bytes);
+#pragma unroll
+      for (int p = 0; p < VPL; ++p) {
+        const int k = lane + 32 * p;
+        if (k < d4_local) {
+          const float4 x = row[k];
+          acc[p].x = fmaf(v, x.x, acc[p].x);
+          acc[p].y = fmaf(v, x.y, acc[p].y);
+          acc[p].z = fmaf(v, x.z, acc[p].z);
+          acc[p].w = fmaf(v, x.w, acc[p].w);
+        }
+      }
+      __syncwarp();                                           // every lane is done with the slot: it may be refilled
+      const int tn = t + SLOTS;
+      const int cn = __shfl_sync(0xffffffffu, my_col, tn & 31);
+      if (tn < cnt && lane == 0) bulk_row_to_smem(slots + s * slot_bytes, Hc + (int64_t)cn * d4, slot_bytes, bars + s);
+      if (++s == SLOTS) s = 0;
+    }
+  }
+}
+
+template <int VPL, int WARPS, int SLOTS>
+__global__ void __launch_bounds__(WARPS * 32)
+spmm_bulk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                 int64_t n_rows, const float* __restrict__ H, int d4, int chunk0, Epilogue ep, int thresh,
+                 const int32_t* __restrict__ seg_begin, const int32_t* __restrict__ seg_end, int64_t n_seg,
+                 float* __restrict__ seg_scratch) {
+  extern __shared__ __align__(128) unsigned char spmm_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int d4_local = min(d4 - chunk0, 32 * VPL);
+  const uint32_t slot_bytes = (uint32_t)d4_local * 16u;
+  unsigned char* slots = spmm_smem + (size_t)wib * SLOTS * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(spmm_smem + (size_t)WARPS * SLOTS * slot_bytes) + wib * SLOTS;
+  if (lane == 0) {
+    for (int i = 0; i < SLOTS; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t w = blockIdx.x * (int64_t)WARPS + wib;
+  if (w >= n_rows + n_seg) return;
+  const Policies pol = make_policies(false);
+  const float4* Hc = reinterpret_cast<const float4*>(H) + chunk0;
+  float4 acc[VPL];
+#pragma unroll
+  for (int p = 0; p < VPL; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t ph = 0;
+  if (w < n_rows) {
+    const int b = rowptr[w], e = rowptr[w + 1];
+    if (e - b > thresh) return;
+    gather_rows_bulk<VPL, SLOTS>(col, val, Hc, d4, d4_local, b, e, lane, slots, slot_bytes, bars, ph, acc);
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) {
+      const int k = lane + 32 * p;
+      if (k < d4_local) {
+        const int64_t off4 = w * d4 + chunk0 + k;
+        const float4 r = apply_epilogue(ep, acc[p], off4, pol);
+        st_once_f4(reinterpret_cast<float4*>(ep.out) + off4, r, pol);
+      }
+    }
+  } else {
+    const int64_t sidx = w - n_rows;
+    gather_rows_bulk<VPL, SLOTS>(col, val, Hc, d4, d4_local, seg_begin[sidx], seg_end[sidx], lane, slots, slot_bytes, bars,
+                                 ph, acc);
+    float4* dst = reinterpret_cast<float4*>(seg_scratch) + sidx * d4 + chunk0;
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) {
+      const int k = lane + 32 * p;
       if (k < d4_local) dst[k] = acc[p];
     }
   }
@@ -383,6 +504,18 @@ static int launch_vec3(const int32_t* rowptr, const int32_t* col, const float* v
                        const int32_t* seg_begin, const int32_t* seg_end, int64_t n_seg, float* seg_scratch,
                        cudaStream_t s) {
   int64_t warps = n_rows + n_seg;
+  if (g_tune_spmm_bulk > 0) {
+    constexpr int BW = 4, BS = 12;
+    const int d4_local = std::min(d4 - chunk0, 32 * VPL);
+    const size_t smem = (size_t)BW * BS * d4_local * 16 + (size_t)BW * BS * 8;
+    auto kern = spmm_bulk_kernel<VPL, BW, BS>;
+    static PerDeviceOnce once;
+    EG_SET_SMEM_ONCE(once, EG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BW * BS * (32 * VPL * 16 + 8))));
+    kern<<<(unsigned)ceil_div(warps, BW), BW * 32, smem, s>>>(rowptr, col, val, n_rows, H, d4, chunk0, ep, thresh, seg_begin,
+                                                              seg_end, n_seg, seg_scratch);
+    EG_LAUNCHED();
+    return EG_OK;
+  }
   if (g_tune_spmm_persist > 0) {
     int64_t want = ceil_div(warps, 8);
     unsigned pgrid = (unsigned)std::min<int64_t>(want, (int64_t)kNumSMs * g_tune_spmm_persist);
