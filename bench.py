@@ -488,6 +488,8 @@ def run_ours(args):
     model = UEAModel(model_args(kg["n"], dev, local)).to(dev)
     params = list(model.parameters())
     opt = torch.optim.Adam(params, lr=1e-3)
+    # N > 1: every parameter's gradient is all-reduced from its autograd hook while the rest of the backward runs
+    grad_sync = parallel.OverlappedGradSync(params) if world > 1 else None
     data = {"e1": kg["e1"], "e2": kg["e2"], "index1": np.arange(kg["e1"]), "index2": np.arange(kg["e2"]) + kg["e1"]}
     bsz, iters = args.bsz, args.sinkhorn_iters
     gen = torch.Generator(device=dev)
@@ -507,8 +509,8 @@ def run_ours(args):
         # late in training and stop sooner — that would make the timed work depend on the training state.
         loss = model.get_loss_wassertein(out, data, bsz, numItermax=iters, stopThr=-1.0, sample=sample)
         loss.backward()
-        if world > 1:
-            parallel.allreduce_grads(params)
+        if grad_sync is not None:
+            grad_sync.finish()
         opt.step()
         return loss
 
