@@ -237,3 +237,22 @@ def test_mrr_from_ranks(dev):
     assert abs(m["MRR_l"] - float(np.mean(1.0 / (rr + 1)))) < 1e-12
     assert abs(m["MRR_r"] - float(np.mean(1.0 / (cr + 1)))) < 1e-12
     assert list(m.keys()) == ["Hits@1_l", "Hits@10_l", "Hits@1_r", "Hits@10_r", "MRR_l", "MRR_r"]
+
+
+def test_sharded_adjacency_halo_single_process(dev):
+    """parallel.ShardedAdjacency(halo=True) in a one-rank world: the remapped CSR over [own rows | fetched rows] (nothing
+    to fetch) must reproduce the plain SpMM and the layer gradients; halo="auto" keeps the plan (no remote rows)."""
+    from gnn_mtl_b200 import ops, parallel as par
+    from gnn_mtl_b200.adjacency import DeviceAdjacency
+    from gnn_mtl_b200.synth import make_kg_pair
+    kg = make_kg_pair("tiny", dim=64)
+    full = DeviceAdjacency.from_triples(kg["n"], kg["triples"], device=dev)
+    sh = par.ShardedAdjacency(full, halo=True)
+    assert sh.halo and sh.plan.n_need == 0 and sh.r0 == 0 and sh.r1 == kg["n"]
+    H = torch.randn(kg["n"], 64, device=dev)
+    want = ops.spmm(full.csr, H)[0]
+    got = ops.spmm(sh.csr, sh.gather(H))[0]
+    assert torch.equal(got, want)
+    got_t = ops.spmm(sh.csr_t, sh.gather(H, transposed=True))[0]
+    assert torch.equal(got_t, ops.spmm(full.csr_t, H)[0])
+    assert par.ShardedAdjacency(full, halo="auto").halo
