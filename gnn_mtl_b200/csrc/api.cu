@@ -5,7 +5,7 @@ namespace eg {
 std::atomic<int64_t> g_launches{0};
 thread_local int t_last_cuda_error = 0;
 // tuning / diagnostic knobs owned by the kernels' translation units
-extern int g_tune_unroll, g_tune_warps, g_tune_hints, g_tune_spmm_persist, g_tune_spmm_slab, g_tune_spmm_bulk;                       // spmm.cu
+extern int g_tune_unroll, g_tune_warps, g_tune_hints, g_tune_spmm_persist, g_tune_spmm_slab, g_tune_spmm_bulk, g_tune_spmm_dynamic;                       // spmm.cu
 extern int g_tune_persistent, g_tune_resident, g_tune_onchip, g_tune_scaling, g_tune_tile2d;     // sinkhorn_dense.cu
 extern int g_tune_absorb_milli, g_tune_force_fallback;
 extern int g_tune_l1_filter;                                                                      // eval_l1.cu
@@ -58,6 +58,7 @@ int eg_debug_set(int key, int value) {
     case 13: eg::g_tune_l1_filter = value; break;
     case 14: eg::g_tune_spmm_slab = value; break;
     case 16: eg::g_tune_spmm_bulk = value; break;
+    case 17: eg::g_tune_spmm_dynamic = value; break;
     default: return EG_ERR_INVALID;
   }
   return EG_OK;

@@ -24,6 +24,7 @@ int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelin
 int g_tune_spmm_slab = 0;   // eg_debug_set(14, v): v in {32, 64}: walk the feature columns in slabs of v float4 (one launch
                             // per slab, rows inner) so that a slab of H stays L2-resident; 0: as wide as the kernel allows
 int g_tune_hints = 0;       // L2 eviction-priority hints (gathers evict_last, streams evict_first): no measured gain
+int g_tune_spmm_dynamic = 0;  // eg_debug_set(17, 1): the persistent SpMM hands out rows through an atomic counter
 int g_tune_spmm_bulk = 0;   // eg_debug_set(16, 1): neighbour rows fetched by cp.async.bulk into shared memory (spmm_bulk_kernel)
 
 struct Epilogue {
@@ -354,12 +355,20 @@ spmm_persist_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
                     const float* __restrict__ val, int64_t n_rows, const float* __restrict__ H, int d4,
                     int chunk0, Epilogue ep, int thresh, const int32_t* __restrict__ seg_begin,
                     const int32_t* __restrict__ seg_end, int64_t n_seg, float* __restrict__ seg_scratch,
-                    int hints) {
+                    int hints, unsigned long long* __restrict__ next_item) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * 8;
   const int64_t total = n_rows + n_seg;
   int64_t w = blockIdx.x * (int64_t)8 + (threadIdx.x >> 5);
   if (w >= total) return;
+  // next_item != null: work items are handed out by an atomic counter (first-come first-served: no row-length
+  // imbalance between warps) instead of the static round-robin; the counter starts at the number of warps in the grid
+  auto grab = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(next_item, 1ull);
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t w_after = next_item ? grab() : w + stride;        // the item after this one (fetched one item ahead)
   const Policies pol = make_policies(hints != 0);
   const float4* Hc = reinterpret_cast<const float4*>(H) + chunk0;
   const int d4_local = min(d4 - chunk0, 32 * VPL);
@@ -379,8 +388,9 @@ spmm_persist_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restric
   float my_val = 0.f;
   if (b + lane < e) { my_col = ld_stream_i32(col + b + lane); my_val = ld_stream_f32(val + b + lane); }
   while (true) {
-    const int64_t wn = w + stride;
+    const int64_t wn = w_after;
     const bool has_next = wn < total;
+    if (has_next) w_after = next_item ? grab() : wn + stride;
     int nb = 0, ne = 0;
     if (has_next) bounds(wn, nb, ne);                        // independent loads, issued before the gathers
     float4 acc[VPL];
@@ -519,8 +529,19 @@ static int launch_vec3(const int32_t* rowptr, const int32_t* col, const float* v
   if (g_tune_spmm_persist > 0) {
     int64_t want = ceil_div(warps, 8);
     unsigned pgrid = (unsigned)std::min<int64_t>(want, (int64_t)kNumSMs * g_tune_spmm_persist);
+    unsigned long long* counter = nullptr;
+    if (g_tune_spmm_dynamic) {
+      static unsigned long long* dev_counter[64] = {};
+      int dev = 0;
+      EG_CUDA(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64) return EG_ERR_UNSUPPORTED;
+      if (!dev_counter[dev]) EG_CUDA(cudaMalloc(&dev_counter[dev], sizeof(unsigned long long)));
+      counter = dev_counter[dev];
+      const unsigned long long first = (unsigned long long)pgrid * 8ull;
+      EG_CUDA(cudaMemcpyAsync(counter, &first, sizeof(first), cudaMemcpyHostToDevice, s));
+    }
     spmm_persist_kernel<VPL, UNROLL><<<pgrid, 256, 0, s>>>(rowptr, col, val, n_rows, H, d4, chunk0, ep, thresh,
-                                                           seg_begin, seg_end, n_seg, seg_scratch, g_tune_hints);
+                                                           seg_begin, seg_end, n_seg, seg_scratch, g_tune_hints, counter);
     EG_LAUNCHED();
     return EG_OK;
   }

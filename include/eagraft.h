@@ -59,7 +59,8 @@ void eg_launch_count_reset(void);
  *     4 resident rows on/off, 5 on-chip fp32 Sinkhorn on/off, 6 persistent SpMM CTAs per SM, 7 scaling-domain
  *     continuation on/off, 10 fold threshold (|log2| x 1000), 11 force the log-domain redo, 12 2-D tiled scaling
  *     kernel on/off (off: row-block kernel), 13 fp32 candidate filter of the L1 rank kernels on/off, 14 SpMM feature
- *     slab width in float4 (0 / 32 / 64), 16 SpMM neighbour rows through cp.async.bulk + shared memory on/off
+ *     slab width in float4 (0 / 32 / 64), 16 SpMM neighbour rows through cp.async.bulk + shared memory on/off,
+ *     17 persistent SpMM (knob 6) hands out rows through an atomic counter on/off
  *   query (value ignored): 8 scaling-domain solves redone in the log domain so far, 9 fold steps so far
  * Queries 8/9 read device counters and synchronise the device. */
 int eg_debug_set(int key, int value);
