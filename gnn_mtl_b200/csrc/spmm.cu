@@ -18,7 +18,8 @@ namespace eg {
 constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
 
 // Tuning knobs (defaults chosen from the ncu study in profiles/); eg_debug_set() overrides them.
-int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each)
+int g_tune_unroll = 0;      // neighbour rows in flight per warp (x VPL float4 each); 0 = by row width: 4 up to 64 float4
+                            // per row (d <= 256: 0.218 vs 0.257 ms at d = 128), else 2 (d = 300: 0.480 vs 0.486 ms)
 int g_tune_warps = 4;       // warps (= rows) per CTA
 int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelined SpMM with n CTAs per SM
 int g_tune_spmm_slab = 0;   // eg_debug_set(14, v): v in {32, 64}: walk the feature columns in slabs of v float4 (one launch
@@ -558,8 +559,9 @@ static int launch_vec(const int32_t* rowptr, const int32_t* col, const float* va
                       const float* H, int d4, int chunk0, const Epilogue& ep, int thresh,
                       const int32_t* seg_begin, const int32_t* seg_end,
                       int64_t n_seg, float* seg_scratch, cudaStream_t s) {
+  const int unroll = g_tune_unroll > 0 ? g_tune_unroll : (VPL <= 2 ? 4 : 2);
 #define EG_SPMM_CASE(U, W)                                                                              \
-  if (g_tune_unroll == U && g_tune_warps == W)                                                          \
+  if (unroll == U && g_tune_warps == W)                                                          \
     return launch_vec3<VPL, U, W>(rowptr, col, val, n_rows, H, d4, chunk0, ep, thresh, seg_begin, seg_end, \
                                   n_seg, seg_scratch, s);
   EG_SPMM_CASE(4, 8) EG_SPMM_CASE(2, 8) EG_SPMM_CASE(4, 4) EG_SPMM_CASE(2, 4) EG_SPMM_CASE(1, 8) EG_SPMM_CASE(8, 4)

@@ -55,7 +55,7 @@ void eg_launch_count_reset(void);
  * never call it and every knob defaults to the shipping kernel.  The knobs are process-global plain ints, so —
  * unlike every other entry point, which may be called concurrently from several host threads on different
  * streams — this call must not race with calls that are inside the library.
- *   set (returns EG_OK):  0/1 SpMM rows-in-flight / warps per CTA, 2 SpMM L2 hints, 3 persistent Sinkhorn on/off,
+ *   set (returns EG_OK):  0/1 SpMM rows-in-flight (0 = chosen by row width) / warps per CTA, 2 SpMM L2 hints, 3 persistent Sinkhorn on/off,
  *     4 resident rows on/off, 5 on-chip fp32 Sinkhorn on/off, 6 persistent SpMM CTAs per SM, 7 scaling-domain
  *     continuation on/off, 10 fold threshold (|log2| x 1000), 11 force the log-domain redo, 12 2-D tiled scaling
  *     kernel on/off (off: row-block kernel), 13 fp32 candidate filter of the L1 rank kernels on/off, 14 SpMM feature
