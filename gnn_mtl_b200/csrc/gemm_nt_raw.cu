@@ -212,6 +212,9 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       const uint32_t idesc = make_idesc(BM, bn);
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       long long w_a = 0, w_b = 0, w_tmem = 0, t_issue = 0, n_kb = 0;
+      uint32_t ready = 0;                                   // answer of the phase test started one k-block earlier
+      unsigned long long g0 = 0; long long k0 = 0;
+      if (dbg_on) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0)); k0 = clock64(); }
       for (int t = 0; t < n_tiles; ++t) {
         const int buf = t & 1;
         const long long c0 = clock64();
@@ -222,7 +225,7 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           const long long c1 = clock64();
           const long long c2 = c1;
-          mbar_wait(&full_b[sb], phb);
+          if (!ready) mbar_wait(&full_b[sb], phb);
           const long long c3 = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(b_base + sb * B_STAGE);
@@ -231,6 +234,11 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
           const uint64_t b_hi = make_smem_desc(st);
           const uint64_t b_lo = make_smem_desc(st + B_BYTES);
           const int k_steps = k_steps_of(kb);
+          // start the test of the NEXT stage now; its latency runs under the (queue-blocked) issue of these MMAs
+          {
+            const int sn = (sb + 1 == SB) ? 0 : sb + 1;
+            ready = mbar_test(&full_b[sn], (sb + 1 == SB) ? (phb ^ 1u) : phb);
+          }
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             if (k >= k_steps) break;
@@ -250,6 +258,8 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
         atomicAdd(p.dbg + 4, (unsigned long long)w_a); atomicAdd(p.dbg + 5, (unsigned long long)w_b);
         atomicAdd(p.dbg + 6, (unsigned long long)t_issue); atomicAdd(p.dbg + 7, (unsigned long long)n_kb);
         atomicAdd(p.dbg + 8, (unsigned long long)w_tmem);
+        unsigned long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        atomicAdd(p.dbg + 10, (unsigned long long)(clock64() - k0)); atomicAdd(p.dbg + 11, g1 - g0);
       }
     }
   } else if (warp >= 8) {
@@ -409,6 +419,8 @@ int gemm_nt_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t 
                     "waits accumulator %.0f per tile\n",
             h[7], bn, h[0] / nk, h[9] / nk, h[1] / nk, h[2] / nk, h[3] / nk, h[4] / nk, h[5] / nk, h[6] / nk,
             (double)h[8] / std::max(1.0, nk / p.k_blocks));
+    fprintf(stderr, "[eagraft] gemm_nt_raw CTA 0: %llu SM cycles in %llu ns of the issuing thread's loop = %.0f MHz\n", h[10], h[11],
+            h[11] ? 1e3 * (double)h[10] / (double)h[11] : 0.0);
   }
   return EG_OK;
 }
