@@ -18,8 +18,9 @@ namespace eg {
 constexpr int kWarpsPerBlock = 8;   // scalar fallback kernel only
 
 // Tuning knobs (defaults chosen from the ncu study in profiles/); eg_debug_set() overrides them.
-int g_tune_unroll = 0;      // neighbour rows in flight per warp (x VPL float4 each); 0 = by row width: 4 up to 64 float4
-                            // per row (d <= 256: 0.218 vs 0.257 ms at d = 128), else 2 (d = 300: 0.480 vs 0.486 ms)
+int g_tune_unroll = 2;      // neighbour rows in flight per warp (x VPL float4 each).  0 = by row width (4 up to 64 float4 per
+                            // row): wins on the benchmark graph at d = 128 (0.218 vs 0.257 ms, ~11 neighbours per row) but
+                            // loses on the 10M-node power-law graph (5.78 vs 5.40 ms, ~5 per row), so 2 stays the default
 int g_tune_warps = 4;       // warps (= rows) per CTA
 int g_tune_spmm_persist = 0;  // eg_debug_set(6, n): n > 0 -> persistent pipelined SpMM with n CTAs per SM
 int g_tune_spmm_slab = 0;   // eg_debug_set(14, v): v in {32, 64}: walk the feature columns in slabs of v float4 (one launch

@@ -34,4 +34,4 @@ for d in (300, 128):
                 t1 = bench(lambda: ops.spmm(c, H)); t2 = bench(lambda: ops.spmm(c, H, _lib.ACT_RELU, g, xr, True))
                 print("d=%d persist %d CTAs/SM dynamic %d unroll %d: plain %.3f ms fused+save %.3f ms identical %s" %
                       (d, persist, dyn, unroll, t1, t2, same), flush=True)
-    dbg(6, 0); dbg(17, 0); dbg(0, 0)
+    dbg(6, 0); dbg(17, 0); dbg(0, 2)

@@ -25,4 +25,4 @@ for d in (300, 128):
         dbg(0, unroll); dbg(1, warps)
         t1 = bench(lambda: ops.spmm(c, H)); t2 = bench(lambda: ops.spmm(c, H, _lib.ACT_RELU, g, xr, True))
         print("d=%d unroll %d warps %d: plain %.3f ms fused+save %.3f ms" % (d, unroll, warps, t1, t2), flush=True)
-    dbg(0, 0); dbg(1, 4)
+    dbg(0, 2); dbg(1, 4)
