@@ -489,7 +489,9 @@ def run_ours(args):
     params = list(model.parameters())
     opt = torch.optim.Adam(params, lr=1e-3)
     # N > 1: every parameter's gradient is all-reduced from its autograd hook while the rest of the backward runs
-    grad_sync = parallel.OverlappedGradSync(params) if world > 1 else None
+    # (EG_BENCH_FLAT_ALLREDUCE=1: one flat all-reduce after backward instead — measurement switch)
+    flat_sync = world > 1 and os.environ.get("EG_BENCH_FLAT_ALLREDUCE") == "1"
+    grad_sync = parallel.OverlappedGradSync(params) if (world > 1 and not flat_sync) else None
     data = {"e1": kg["e1"], "e2": kg["e2"], "index1": np.arange(kg["e1"]), "index2": np.arange(kg["e2"]) + kg["e1"]}
     bsz, iters = args.bsz, args.sinkhorn_iters
     gen = torch.Generator(device=dev)
@@ -511,6 +513,8 @@ def run_ours(args):
         loss.backward()
         if grad_sync is not None:
             grad_sync.finish()
+        elif flat_sync:
+            parallel.allreduce_grads(params)
         opt.step()
         return loss
 
