@@ -1,31 +1,19 @@
-// NT 3xTF32 GEMM of the layers with the A operand fed RAW (fp32): its hi/lo split happens inside the kernel.
+// 2-SM version of the raw-operand NT 3xTF32 GEMM (gemm_nt_raw.cu): a pair of CTAs on the two SMs of a TPC computes one
+// 256 x bn output tile with tcgen05.mma.cta_group::2.
 //
-//   C[m, n] = [A1 | A2][m, k1 + k2] · B[n, ·]ᵀ + bias          (x·G + c, x·[W;Gᵀ]ᵀ + [b|c], dx = [dH | d_gate]·[Wᵀ | G]ᵀ;
-//                                                                layers/layers.py:61,69 and their input gradient)
+// Why: the single-SM kernels are bound by the shared-memory port — a 128 x 160 x 8 tf32 MMA is 80 cycles of math but
+// fetches 9.2 KB of 4-byte operands from shared memory (72 cycles at 128 B/clk) next to the TMA fill of the same
+// memory (profiles/README.md, round 2).  In a CTA pair every SM stages only HALF of the B tile (the tensor cores
+// exchange the halves), A comes from each SM's own tensor memory (the raw-operand path: fp32 tile -> converter warps
+// -> hi | lo pair in TMEM), so per MMA an SM reads 2.5 KB of B from shared memory instead of 9.2 KB of A and B.
 //
-// What the per-role timers of this kernel's first versions showed (tools/gemm_raw_dbg.py) and what the split-operand
-// kernel (lse_tc_kernel<2>, sinkhorn_tc.cu) therefore suffers from: six MMAs of a k-block occupy the tensor pipe for
-// 480-620 cycles, but a k-block came by only every 1250 cycles, because a TMA round trip under load takes ~5000 cycles
-// and shared memory holds just four 36 KB stages of hi/lo operands: the ring is LATENCY bound, and its depth is
-// bought with bytes.  So this kernel makes the stage small and the ring deep:
-//   * A (the operand that streams from HBM) arrives RAW: 8 KB per k-block, ten stages in flight;
-//   * four converter warps turn row r of a raw stage into hi = tf32(x), lo = tf32(x - hi) (the roundings of
-//     eg_split_tf32: results are bit-identical) and write the pair straight into TENSOR MEMORY — tcgen05.mma takes
-//     its A operand from TMEM (lane = row, one 32-bit column per K element), and the thread that owns row r holds
-//     exactly lane r's 16 values.  The A pair never goes back to shared memory;
-//   * B (the weights: L2 resident, ~1000-cycle round trips) keeps its host-made hi/lo pair, five 22 KB stages that
-//     share their ready / free barriers with five 32-column A stages in TMEM (one wait and one commit per k-block);
-//   * no eg_split_tf32 pass over A at all (a launch and 0.7 GB of HBM traffic per operand).
-//
-// 384 threads: warp 0 = TMA producer of A, warp 2 = TMA producer of B, warp 1 = TMEM owner + MMA issuer, warps 4-7 =
-// epilogue, warps 8-11 = A converters (TMEM lane quadrant = warp % 4 for both).  TMEM: two accumulators of <= 176
-// columns + 5 A stages of 32 columns = 512.  Persistent over row tiles like the split-operand kernel.
-//
-// Measured (tools/gemm_raw_check.py, tools/gemm_raw_dbg.py; [200k, 300] operands): per k-block the issuing thread waits
-// 210 cycles for a ready stage and spends 536 in the (queue-blocked) issue of its six MMAs, i.e. the tensor pipe is busy
-// 64-72 % of the cycles; 0.248 ms at n = 300 (split-operand kernel 0.254 + 0.11 ms of split launch), dx (K = 2 x 300)
-// 0.459 ms (0.468 + 0.11).  At n = 600 the 176-column cap costs a fourth column tile (0.475 vs 0.438 ms): that
-// shape stays on the split-operand kernel.
+// Protocol (rank 0 = leader: the only issuer of MMAs):
+//   * A: each CTA loads and converts its own 128 rows — rings and barriers are local;
+//   * B: each CTA loads its half (bn/2 rows) of the host-made hi / lo pair with the cta_group::2 TMA form, whose bytes
+//     count on the LEADER's ready barrier; the leader's B producer posts the expected bytes of both halves;
+//   * ready[s] (leader) = 4 + 4 converter-warp arrivals (the peer's arrive remotely) + that expect_tx arrival;
+//   * free[s], tfull[b]: multicast tcgen05.commit.cta_group::2 -> both CTAs' barriers;
+//   * tempty[b] (leader) = 4 + 4 epilogue-warp arrivals; every CTA drains its own 128 accumulator rows.
 #include <cuda.h>
 
 #include <algorithm>
@@ -36,19 +24,24 @@
 #include "tc_common.cuh"
 
 namespace eg {
-namespace ntr {
+namespace ntr2 {
 using namespace ::eg::tc;
 
 constexpr int BM = 128;
-constexpr int BNMAX = 176;                   // 2 accumulators x 176 + 5 A stages x 32 columns = 512 TMEM columns
+// Columns per tile.  MMAs that accumulate into the same tile issue no faster than one per ~121 cycles whatever N is up
+// to 192 (tools/mma_rate.cu: dependent tf32 MMAs with A from tensor memory; 128 x 160 x 8 is 80 cycles of math), so what
+// counts is the NUMBER of column tiles per row, not their width: equal tiles (n = 600 -> 4 x 160, n = 300 -> 2 x 160)
+// measured faster than 192-wide tiles plus a narrow last one (0.425 / 0.225 ms against 0.440 / 0.235 ms at 200k rows).
+constexpr int BNMAX = 160;                   // 2 accumulators x 160 + 5 A stages x 32 columns = 480 of 512 TMEM columns;
+                                             // UMMA N of a 256-row pair MMA must be a multiple of 32
 constexpr int BK = 16;                       // fp32 per k-block = one 64-byte swizzle row
 constexpr int UK = 8;
 constexpr int ROW_BYTES = BK * 4;
 constexpr int RA = 10;                       // raw A stages in flight (10 x 8 KB)
-constexpr int SB = 5;                        // operand stages the MMAs read: B pair in shared memory (5 x 22 KB) +
-constexpr int SA = SB;                       // A pair in tensor memory (5 x 32 columns), one barrier pair for both
+constexpr int SB = 5;                        // operand stages the MMAs read: this CTA's half of the B pair in shared memory
+constexpr int SA = SB;                       // (5 x 10 KB) + its A pair in tensor memory (5 x 32 columns), one barrier pair
 constexpr int A_BYTES = BM * ROW_BYTES;      // 8 KB
-constexpr int B_BYTES = BNMAX * ROW_BYTES;   // 11 KB
+constexpr int B_BYTES = (BNMAX / 2) * ROW_BYTES;   // 5 KB: this CTA's half of the B tile
 constexpr int B_STAGE = 2 * B_BYTES;
 constexpr int TMEM_A0 = 2 * BNMAX;           // first TMEM column of the A stages
 constexpr int NUM_THREADS = 384;
@@ -59,7 +52,7 @@ struct Params {
   int64_t m, n;
   int k1, k2;              // K extents of the two A operands (k2 = 0: one operand)
   int kb1, k_blocks;       // k-blocks of A1, total
-  int bn;                  // columns per tile (multiple of 16, <= 208)
+  int bn;                  // columns per full tile (multiple of 32, <= BNMAX); the last tile of a row may be narrower
   const float* bias;       // [n] or null
   float* out1; float* out2;
   int64_t ld1, ld2, n1;
@@ -95,14 +88,14 @@ __device__ __forceinline__ void split4(const float4& x, float4& h, float4& l) {
   h = make_float4(hs[0], hs[1], hs[2], hs[3]);
   l = make_float4(ls[0], ls[1], ls[2], ls[3]);
 }
-// D[tmem] (+)= A[tmem] * B[smem]: A operand read from tensor memory (lane = row, one column per tf32 element)
+// D[tmem of both CTAs] (+)= A[tmem of both CTAs] * B[halves in both CTAs' smem]; issued by the leader only
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -116,8 +109,46 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
                : "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Arrive on a barrier of the LEADER CTA (rank 0) from the peer.  Default (CTA-scope) semantics on purpose: the data the
+// arrival publishes is tensor memory written with tcgen05.st + wait::st, which no memory fence covers anyway, and the
+// cluster-scope release form costs a MEMBAR.ALL.GPU per arrival (measured: 1400 cycles per k-block in the converters).
+__device__ __forceinline__ void arrive_on_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(bar), 0u)) : "memory");
+}
+// TMA load whose bytes complete on the LEADER's barrier (peer bit of the barrier address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner),
+        "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)0x3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_nt_raw2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const Params p) {
   extern __shared__ uint8_t smem_raw_[];
@@ -138,11 +169,19 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0;
   const int bn = p.bn;
   const int n_btiles = (int)((p.n + bn - 1) / bn);
-  const int n_rtiles = (int)((p.m + BM - 1) / BM);
-  const int my_rtiles = (n_rtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = cluster_ctarank();               // 0 = leader (issues the MMAs), 1 = peer
+  const bool leader = crank == 0;
+  const int n_clusters = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+  const int n_rtiles = (int)((p.m + 2 * BM - 1) / (2 * BM));            // 256-row tiles of the pair
+  const int my_rtiles = (n_rtiles - cluster_id + n_clusters - 1) / n_clusters;
   const int n_tiles = my_rtiles * n_btiles;
-  auto tile_i0 = [&](int t) -> int64_t { return ((int64_t)blockIdx.x + (int64_t)(t / n_btiles) * gridDim.x) * BM; };
+  // first row of THIS CTA's half of pair tile t
+  auto tile_i0 = [&](int t) -> int64_t {
+    return ((int64_t)cluster_id + (int64_t)(t / n_btiles) * n_clusters) * (2 * BM) + (int64_t)crank * BM;
+  };
   auto tile_j0 = [&](int t) -> int { return (t % n_btiles) * bn; };
+  // columns of tile t: the row's last tile covers what is left, rounded up to the pair MMA's granularity of 32
+  auto tile_bn = [&](int t) -> int { return min(bn, (int)((p.n - tile_j0(t) + 31) / 32) * 32); };
   // live k-steps of k-block kb: the last block of an operand may reach past its K extent (TMA zero-fills it)
   auto k_steps_of = [&](int kb) -> int {
     const int valid = (kb < p.kb1) ? p.k1 - kb * BK : p.k2 - (kb - p.kb1) * BK;
@@ -153,17 +192,18 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     for (int s = 0; s < RA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 4); }
     // one "ready" barrier per operand stage: 4 converter warps (A pair in TMEM) + the B producer's expect_tx arrival;
     // one "free" barrier: the commit of the MMAs that read the stage (waited on by the converters and the B producer)
-    for (int s = 0; s < SB; ++s) { mbar_init(&full_b[s], 5); mbar_init(&empty_b[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&full_b[s], 9); mbar_init(&empty_b[s], 1); }   // 4 + 4 converter warps + expect_tx
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }      // both CTAs' epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync();                                          // both CTAs' barriers and TMEM exist before any cross-CTA signal
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -198,19 +238,21 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
           mbar_wait(&empty_b[s], ph ^ 1);
           if (dbg_on) w += clock64() - c0;
           uint8_t* st = b_base + s * B_STAGE;
-          mbar_expect_tx(&full_b[s], 2 * bn * ROW_BYTES);
-          tma_load_2d(st, &map_b_hi, &full_b[s], kb * BK, j0);              // B's parts are padded to 16 columns each
-          tma_load_2d(st + B_BYTES, &map_b_lo, &full_b[s], kb * BK, j0);
+          // the leader's barrier counts the bytes of both CTAs' halves (hi + lo, bn / 2 rows each, per CTA)
+          if (leader) mbar_expect_tx(&full_b[s], 2 * bn * ROW_BYTES);
+          const int jh = j0 + (int)crank * (tile_bn(t) / 2);              // the box stays bn / 2 rows; a narrow tile ignores the rest
+          tma_load_2d_pair(st, &map_b_hi, &full_b[s], kb * BK, jh);         // B's parts are padded to 16 columns each
+          tma_load_2d_pair(st + B_BYTES, &map_b_lo, &full_b[s], kb * BK, jh);
           if (++s == SB) { s = 0; ph ^= 1; }
         }
       }
       if (dbg_on) atomicAdd(p.dbg + 9, (unsigned long long)w);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues (elect_one) ==========
-    {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop with warp-uniform values and one elected lane issues (tc_common.cuh, elect_one).
+    if (leader) {
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t idesc = make_idesc(BM, bn);
       int sa = 0, sb = 0; uint32_t phb = 0;
       long long w_b = 0, w_tmem = 0, t_issue = 0, n_kb = 0;
       unsigned long long g0 = 0; long long k0 = 0;
@@ -223,6 +265,7 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
         if (dbg_on) w_tmem += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tbase + (uint32_t)(buf * BNMAX);
+        const uint32_t idesc = make_idesc(2 * BM, tile_bn(t));
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           long long c2 = 0, c3 = 0;
           if (dbg_on) c2 = clock64();
@@ -244,14 +287,14 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               umma_tf32_ts(tmem_d, a_hi + (uint32_t)(k * UK), b_lo + koff, idesc, 1);
               umma_tf32_ts(tmem_d, a_lo + (uint32_t)(k * UK), b_hi + koff, idesc, 1);
             }
-            umma_commit(&empty_b[sb]);
+            umma_commit_pair(&empty_b[sb]);                  // frees the stage in both CTAs
           }
           __syncwarp();
           if (dbg_on) { w_b += c3 - c2; t_issue += clock64() - c3; ++n_kb; }
           if (++sa == SA) sa = 0;
           if (++sb == SB) { sb = 0; phb ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull[buf]);
+        if (elect_one()) umma_commit_pair(&tfull[buf]);
         __syncwarp();
       }
       if (dbg_on && lane == 0) {
@@ -295,10 +338,11 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        // The raw stage is released only here, behind the tensor-memory stores that consumed the loaded registers: an
-        // arrive straight after the loads can overtake them (nothing makes the arrive wait for load data), and the TMA
-        // refill of the stage then races the read — seen as rows holding the k-block 10 stages ahead.
-        if (lane == 0) { mbar_arrive(&empty_a[ra]); mbar_arrive(&full_b[sa]); }
+        // the raw stage is released behind the tensor-memory stores that consumed the loaded registers (see gemm_nt_raw.cu)
+        if (lane == 0) {
+          mbar_arrive(&empty_a[ra]);
+          if (leader) mbar_arrive(&full_b[sa]); else arrive_on_leader(&full_b[sa]);
+        }
         if (dbg_on) { w_raw += c1 - c0; w_spl += c3 - c2; t_work += (c2 - c1) + (clock64() - c3); }
         if (++ra == RA) { ra = 0; phr ^= 1; }
         if (++sa == SA) { sa = 0; phs ^= 1; }
@@ -326,15 +370,16 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       mbar_wait(&tfull[buf], (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BNMAX);
+      const int bn_t = tile_bn(t);
 #pragma unroll 1
-      for (int c0 = 0; c0 < bn; c0 += 32) {
+      for (int c0 = 0; c0 < bn_t; c0 += 32) {
         float dot[32];
         tmem_ld32(taddr + (uint32_t)c0, dot);
         if (trow < p.m) {
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             const int64_t j = j0 + c0 + c;
-            if (j < p.n && c0 + c < bn) {                      // n, n1, bn are multiples of 4 (checked on the host)
+            if (j < p.n) {                      // n, n1, bn are multiples of 4 (checked on the host)
               float4 v = make_float4(dot[c] + bs[c0 + c], dot[c + 1] + bs[c0 + c + 1], dot[c + 2] + bs[c0 + c + 2],
                                      dot[c + 3] + bs[c0 + c + 3]);
               if (p.addend) {
@@ -349,13 +394,14 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) { if (leader) mbar_arrive(&tempty[buf]); else arrive_on_leader(&tempty[buf]); }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync();                    // no remote arrive, multicast commit or pair MMA may still target a CTA that left
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
 }
@@ -374,12 +420,12 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int k, in
   return r == CUDA_SUCCESS ? EG_OK : EG_ERR_INVALID;
 }
 
-}  // namespace ntr
+}  // namespace ntr2
 
-int gemm_nt_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t lda2, int k2, int64_t m,
+int gemm_nt_raw2(const float* A1, int64_t lda1, int k1, const float* A2, int64_t lda2, int k2, int64_t m,
                 const float* B_hi, const float* B_lo, int64_t ldb, int64_t n, const float* bias, const float* addend,
                 int64_t ld_add, float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, cudaStream_t s) {
-  using namespace ntr;
+  using namespace ntr2;
   if (k1 <= 0 || k2 < 0 || n % 4 || n1 % 4 || n1 > n || n1 <= 0 || (n1 < n && !out2)) return EG_ERR_INVALID;
   if (lda1 % 4 || (k2 && lda2 % 4) || ldb % 4 || ld1 % 4 || (out2 && ld2 % 4)) return EG_ERR_INVALID;
   if (((uintptr_t)A1 | (uintptr_t)A2 | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)out1 | (uintptr_t)out2 | (uintptr_t)addend) & 15)
@@ -389,14 +435,14 @@ int gemm_nt_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t 
   const int kb1 = (k1 + BK - 1) / BK, kb2 = (k2 + BK - 1) / BK;
   if ((int64_t)(kb1 + kb2) * BK > ldb) return EG_ERR_INVALID;         // B holds the parts back to back, each padded to 16
   const int64_t n_ct = ceil_div(n, (int64_t)BNMAX);
-  const int bn = (int)std::min<int64_t>(BNMAX, ceil_div(ceil_div(n, n_ct), (int64_t)16) * 16);
+  const int bn = (int)std::min<int64_t>(BNMAX, ceil_div(ceil_div(n, n_ct), (int64_t)32) * 32);   // pair MMA: N % 32 == 0
   CUtensorMap ma1, ma2, mbh, mbl;
   int rc;
   if ((rc = make_map(&ma1, A1, m, k1, lda1, BM))) return rc;
   if (k2) { if ((rc = make_map(&ma2, A2, m, k2, lda2, BM))) return rc; }
   else ma2 = ma1;
-  if ((rc = make_map(&mbh, B_hi, n, (kb1 + kb2) * BK, ldb, bn))) return rc;
-  if ((rc = make_map(&mbl, B_lo, n, (kb1 + kb2) * BK, ldb, bn))) return rc;
+  if ((rc = make_map(&mbh, B_hi, n, (kb1 + kb2) * BK, ldb, bn / 2))) return rc;    // one CTA's half of the tile
+  if ((rc = make_map(&mbl, B_lo, n, (kb1 + kb2) * BK, ldb, bn / 2))) return rc;
   Params p{};
   p.m = m; p.n = n; p.k1 = k1; p.k2 = k2; p.kb1 = kb1; p.k_blocks = kb1 + kb2; p.bn = bn;
   p.bias = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
@@ -408,21 +454,21 @@ int gemm_nt_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t 
     p.dbg = dbg_buf;
   }
   static PerDeviceOnce attr_once;
-  EG_SET_SMEM_ONCE(attr_once, EG_CUDA(cudaFuncSetAttribute(gemm_nt_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
-  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(m, BM), kNumSMs);
-  gemm_nt_raw_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma1, ma2, mbh, mbl, p);
+  EG_SET_SMEM_ONCE(attr_once, EG_CUDA(cudaFuncSetAttribute(gemm_nt_raw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+  const unsigned grid = 2u * (unsigned)std::min<int64_t>(ceil_div(m, 2 * BM), kNumSMs / 2);
+  gemm_nt_raw2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma1, ma2, mbh, mbl, p);
   EG_LAUNCHED();
   if (p.dbg) {
     unsigned long long h[16];
     EG_CUDA(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, s));
     EG_CUDA(cudaStreamSynchronize(s));
     const double nk = (double)std::max<unsigned long long>(h[7], 1);
-    fprintf(stderr, "[eagraft] gemm_nt_raw CTA 0, cycles per k-block (%llu k-blocks, bn %d): A producer waits %.0f, B producer waits %.0f | "
+    fprintf(stderr, "[eagraft] gemm_nt_raw2 CTA 0, cycles per k-block (%llu k-blocks, bn %d): A producer waits %.0f, B producer waits %.0f | "
                     "A converter: waits raw %.0f, waits TMEM stage %.0f, works %.0f | issuer: waits A %.0f, waits B %.0f, issues %.0f; "
                     "waits accumulator %.0f per tile\n",
             h[7], bn, h[0] / nk, h[9] / nk, h[1] / nk, h[2] / nk, h[3] / nk, h[4] / nk, h[5] / nk, h[6] / nk,
             (double)h[8] / std::max(1.0, nk / p.k_blocks));
-    fprintf(stderr, "[eagraft] gemm_nt_raw CTA 0: %llu SM cycles in %llu ns of the issuing thread's loop = %.0f MHz\n", h[10], h[11],
+    fprintf(stderr, "[eagraft] gemm_nt_raw2 CTA 0: %llu SM cycles in %llu ns of the issuing thread's loop = %.0f MHz\n", h[10], h[11],
             h[11] ? 1e3 * (double)h[10] / (double)h[11] : 0.0);
   }
   return EG_OK;
@@ -430,26 +476,3 @@ int gemm_nt_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t 
 
 }  // namespace eg
 
-using namespace eg;
-
-namespace eg {
-int g_tune_gemm_pair = 1;    // knob 18: 1 (default) = the CTA-pair (tcgen05.mma.cta_group::2) kernel of gemm_nt_raw2.cu,
-                             // 0 = the single-SM kernel above (same bits; 0.45 / 0.24 ms against 0.39 / 0.21 ms at 200k x 300 -> 600 / 300)
-int gemm_nt_raw2(const float* A1, int64_t lda1, int k1, const float* A2, int64_t lda2, int k2, int64_t m, const float* B_hi,
-                 const float* B_lo, int64_t ldb, int64_t n, const float* bias, const float* addend, int64_t ld_add,
-                 float* out1, int64_t ld1, int64_t n1, float* out2, int64_t ld2, cudaStream_t s);
-}  // namespace eg
-
-extern "C" int eg_gemm_nt_3xtf32_raw(const float* A1, int64_t lda1, int k1, const float* A2, int64_t lda2, int k2, int64_t m,
-                                     const float* B_hi, const float* B_lo, int64_t ldb, int64_t n, const float* bias,
-                                     const float* addend, int64_t ld_add, float* out1, int64_t ld1, int64_t n1,
-                                     float* out2, int64_t ld2, eg_stream_t stream_) {
-  if (m < 0 || n <= 0) return EG_ERR_INVALID;
-  if (m == 0) return EG_OK;
-  if (!A1 || !B_hi || !B_lo || !out1 || (k2 > 0 && !A2)) return EG_ERR_INVALID;
-  if (g_tune_gemm_pair)
-    return gemm_nt_raw2(A1, lda1, k1, A2, lda2, k2, m, B_hi, B_lo, ldb, n, bias, addend, ld_add, out1, ld1, n1, out2, ld2,
-                        as_stream(stream_));
-  return gemm_nt_raw(A1, lda1, k1, A2, lda2, k2, m, B_hi, B_lo, ldb, n, bias, addend, ld_add, out1, ld1, n1, out2, ld2,
-                     as_stream(stream_));
-}

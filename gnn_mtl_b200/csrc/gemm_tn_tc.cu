@@ -127,7 +127,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                                   // whole warp, one elected lane issues (elect_one)
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = make_idesc_mn(BM, BN);
       int s = 0; uint32_t ph = 0;
       const int n_chunks = (n_kb + FLUSH_KB - 1) / FLUSH_KB;
@@ -135,28 +136,32 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int buf = c & 1;
         mbar_wait(&tempty[buf], (uint32_t)(((c >> 1) & 1) ^ 1));      // epilogue has drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+        const uint32_t tmem_d = tbase + (uint32_t)(buf * 256);
         const int kb_hi = min(n_kb, (c + 1) * FLUSH_KB);
         for (int kb = c * FLUSH_KB; kb < kb_hi; ++kb) {
           mbar_wait(&full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint32_t koff = (uint32_t)k * 1024u;               // next 8 rows (two K atoms) inside every box
-            const uint64_t a_hi = make_desc_mn(st + koff);
-            const uint64_t a_lo = make_desc_mn(st + A_TILE_BYTES + koff);
-            const uint64_t b_hi = make_desc_mn(st + 2 * A_TILE_BYTES + koff);
-            const uint64_t b_lo = make_desc_mn(st + 2 * A_TILE_BYTES + B_TILE_BYTES + koff);
-            // small cross terms first, the dominant hi·hi last: what truncation there is hits the small terms
-            umma_tf32(tmem_d, a_hi, b_lo, idesc, (kb != c * FLUSH_KB) || k != 0);
-            umma_tf32(tmem_d, a_lo, b_hi, idesc, 1);
-            umma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint32_t koff = (uint32_t)k * 1024u;             // next 8 rows (two K atoms) inside every box
+              const uint64_t a_hi = make_desc_mn(st + koff);
+              const uint64_t a_lo = make_desc_mn(st + A_TILE_BYTES + koff);
+              const uint64_t b_hi = make_desc_mn(st + 2 * A_TILE_BYTES + koff);
+              const uint64_t b_lo = make_desc_mn(st + 2 * A_TILE_BYTES + B_TILE_BYTES + koff);
+              // small cross terms first, the dominant hi·hi last: what truncation there is hits the small terms
+              umma_tf32(tmem_d, a_hi, b_lo, idesc, (kb != c * FLUSH_KB) || k != 0);
+              umma_tf32(tmem_d, a_lo, b_hi, idesc, 1);
+              umma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[buf]);
+        if (elect_one()) umma_commit(&tfull[buf]);
+        __syncwarp();
       }
     }
   } else {

@@ -203,14 +203,15 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues (elect_one) ==========
+    {
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc(BM, bn);
       int s = 0; uint32_t ph = 0;
       uint32_t chain = 0;                                  // MODE 3: accumulation chains issued so far
       for (int t = 0; t < n_tiles; ++t) {
         int buf = t & 1;
-        uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        uint32_t tmem_d = tbase + (uint32_t)(buf * BN);
         if (MODE != 3) {
           const uint32_t use = (uint32_t)(t >> 1);         // how many times this buffer was used before
           mbar_wait(&tempty[buf], (use & 1) ^ 1);          // epilogue has drained the buffer
@@ -219,7 +220,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           if (MODE == 3) {                                 // a fresh accumulator per k-block, three buffers rotate
             buf = (int)(chain % 3u);                       // (3 x 160 TMEM columns: the MMAs run two chains ahead
-            tmem_d = tmem_base + (uint32_t)(buf * kFlushBN);   //  of the fold, which hides the commit -> wake-up hand-off)
+            tmem_d = tbase + (uint32_t)(buf * kFlushBN);       //  of the fold, which hides the commit -> wake-up hand-off)
             mbar_wait(&tempty[buf], ((chain / 3u) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
@@ -232,19 +233,26 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           const uint64_t b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
           // the last k-block may be partly past d_pad (TMA zero-fills it): skip those k-steps
           const int k_steps = min(BK / UK, (p.d_pad - kb * BK) / UK);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            if (k >= k_steps) break;
-            const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);   // 32 B per k-step, in 16-byte units
-            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, MODE == 3 ? (uint32_t)(k != 0) : (uint32_t)((kb | k) != 0));
-            umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
-            umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
+            for (int k = 0; k < BK / UK; ++k) {
+              if (k >= k_steps) break;
+              const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);   // 32 B per k-step, in 16-byte units
+              umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, MODE == 3 ? (uint32_t)(k != 0) : (uint32_t)((kb | k) != 0));
+              umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
+            }
+            umma_commit(&empty[s]);                           // smem stage reusable once these MMAs retire
+            if (MODE == 3) umma_commit(&tfull[buf]);          // chain complete: the epilogue folds it
           }
-          umma_commit(&empty[s]);                           // smem stage reusable once these MMAs retire
-          if (MODE == 3) { umma_commit(&tfull[buf]); ++chain; }    // chain complete: the epilogue folds it
+          __syncwarp();
+          if (MODE == 3) ++chain;
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (MODE != 3) umma_commit(&tfull[buf]);            // accumulator complete
+        if (MODE != 3) {
+          if (elect_one()) umma_commit(&tfull[buf]);          // accumulator complete
+          __syncwarp();
+        }
       }
     }
   } else {

@@ -43,6 +43,17 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
   return done;
 }
 
+// One lane of a converged warp.  The MMA warps run their loops warp-uniformly and guard only the issue with this: inside
+// an `if (lane == 0)` region the compiler cannot keep MMA operands in uniform registers and wraps every tcgen05.mma in a
+// broadcast loop (ELECT / R2UR.BROADCAST / BRA.U.ANY), about 45 cycles of issue per MMA (tools/mma_rate.cu) — more than
+// half of the 80 cycles a 128 x 160 x 8 tf32 MMA computes for.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}"
+               : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
                                             int c_outer) {
   asm volatile(

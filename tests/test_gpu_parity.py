@@ -591,6 +591,30 @@ def test_gemm_nt_raw_operands_bit_identical(m, k, k2, n, n1, dev):
     assert torch.equal(ops.gemm_nt_raw(parts, B, bias, addend=add), cat(ops.gemm_nt(parts, B, bias)) + add)
 
 
+@pytest.mark.parametrize("pair", [1, 0])
+def test_gemm_nt_raw_both_kernels_and_raw_stage_release(pair, dev):
+    """Both kernels behind eg_gemm_nt_3xtf32_raw — CTA pairs on tcgen05.mma.cta_group::2 (debug knob 18 = 1, the default)
+    and the single-SM kernel (0) — give the split-operand bits at the benched height, on every run.  One column tile per
+    row tile (n = 160) at 200k rows is the shape that exposed an early release of the raw A stage (the arrive that frees
+    the stage overtook the loads of it, and the TMA refill raced the read: a handful of rows per run held the k-block
+    ten stages ahead); the release now sits behind the tensor-memory stores that consume the loaded registers."""
+    from gnn_mtl_b200 import _lib, ops
+    torch.manual_seed(3)
+    m, k = 200000, 300
+    A = torch.randn(m, k, device=dev)
+    try:
+        _lib.lib.eg_debug_set(18, pair)
+        for n in (160, 600):
+            B = torch.randn(n, k, device=dev) * 0.1
+            want = ops.gemm_nt([A], B)
+            for _ in range(3):
+                got = ops.gemm_nt_raw([A], B)
+                bad = int((got != want).any(1).sum())
+                assert bad == 0, "%d rows differ (n = %d, pair = %d)" % (bad, n, pair)
+    finally:
+        _lib.lib.eg_debug_set(18, 1)
+
+
 def test_margin_loss_golden_and_scale(golden_dir, dev):
     """Fused gather + L1 + hinge loss (models/models_ea.py:103-123): value and gradient."""
     from oracle import ea_oracle as orc
