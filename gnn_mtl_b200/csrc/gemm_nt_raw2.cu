@@ -32,14 +32,14 @@ constexpr int BM = 128;
 // to 192 (tools/mma_rate.cu: dependent tf32 MMAs with A from tensor memory; 128 x 160 x 8 is 80 cycles of math), so what
 // counts is the NUMBER of column tiles per row, not their width: equal tiles (n = 600 -> 4 x 160, n = 300 -> 2 x 160)
 // measured faster than 192-wide tiles plus a narrow last one (0.425 / 0.225 ms against 0.440 / 0.235 ms at 200k rows).
-constexpr int BNMAX = 160;                   // 2 accumulators x 160 + 5 A stages x 32 columns = 480 of 512 TMEM columns;
+constexpr int BNMAX = 160;                   // 2 accumulators x 160 + 6 A stages x 32 columns = 512 TMEM columns;
                                              // UMMA N of a 256-row pair MMA must be a multiple of 32
 constexpr int BK = 16;                       // fp32 per k-block = one 64-byte swizzle row
 constexpr int UK = 8;
 constexpr int ROW_BYTES = BK * 4;
 constexpr int RA = 10;                       // raw A stages in flight (10 x 8 KB)
-constexpr int SB = 5;                        // operand stages the MMAs read: this CTA's half of the B pair in shared memory
-constexpr int SA = SB;                       // (5 x 10 KB) + its A pair in tensor memory (5 x 32 columns), one barrier pair
+constexpr int SB = 6;                        // operand stages the MMAs read: this CTA's half of the B pair in shared memory
+constexpr int SA = SB;                       // (6 x 10 KB) + its A pair in tensor memory (6 x 32 columns), one barrier pair
 constexpr int A_BYTES = BM * ROW_BYTES;      // 8 KB
 constexpr int B_BYTES = (BNMAX / 2) * ROW_BYTES;   // 5 KB: this CTA's half of the B tile
 constexpr int B_STAGE = 2 * B_BYTES;

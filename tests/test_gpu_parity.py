@@ -615,6 +615,29 @@ def test_gemm_nt_raw_both_kernels_and_raw_stage_release(pair, dev):
         _lib.lib.eg_debug_set(18, 1)
 
 
+@pytest.mark.parametrize("shape", [(1031, 300), (257, 7), (64, 4)])
+@pytest.mark.parametrize("act_relu,gated", [(True, True), (False, True), (True, False)])
+def test_epilogue_bwd_float4_and_scalar_paths(shape, act_relu, gated, dev):
+    """Backward of the SpMM epilogue (layers/layers.py:65-72: activation, then the highway mix): the float4 kernel
+    (16-byte aligned operands, element count % 4 == 0) and the scalar kernel (anything else) against the formula."""
+    from gnn_mtl_b200 import _lib, ops
+    torch.manual_seed(shape[0] + shape[1])
+    g = torch.randn(*shape, device=dev)
+    a = torch.randn(*shape, device=dev)
+    pre = torch.randn(*shape, device=dev) if gated else None
+    x = torch.randn(*shape, device=dev) if gated else None
+    act = _lib.ACT_RELU if act_relu else _lib.ACT_IDENTITY
+    dS, dG, dX = ops.epilogue_bwd(g, a, pre, x, act, True, True)
+    t = torch.sigmoid(pre) if gated else torch.ones_like(g)
+    want_dS = g * t
+    if act_relu:
+        want_dS = torch.where(a > 0, want_dS, torch.zeros_like(want_dS))
+    assert torch.allclose(dS, want_dS, rtol=1e-6, atol=1e-7)
+    if gated:
+        assert torch.allclose(dG, g * (a - x) * (t * (1 - t)), rtol=1e-5, atol=1e-7)
+        assert torch.allclose(dX, g * (1 - t), rtol=1e-5, atol=1e-7)
+
+
 def test_margin_loss_golden_and_scale(golden_dir, dev):
     """Fused gather + L1 + hinge loss (models/models_ea.py:103-123): value and gradient."""
     from oracle import ea_oracle as orc
