@@ -691,7 +691,7 @@ def run_ours(args):
         # dense TF32 rate = half the dense bf16 rate of the same tensor pipe: MEASURED_PEAKS.json's bf16 burst / 2
         tf_peak = float(peaks.get("bf16_tflops", 1640.2)) / 2.0
         ach = 3 * 2.0 * nf * nf * 300 / ms_f / 1e9
-        fused = {"kernel": "lse_tc_kernel<0> (TMA + tcgen05 3xTF32 cost tiles + online LSE), 30000x30000x300 half-sweep, "
+        fused = {"kernel": "lse_tc_kernel<0, pair> (TMA + tcgen05.mma.cta_group::2 3xTF32 cost tiles on CTA pairs + online LSE), 30000x30000x300 half-sweep, "
                            "aligned-pair data (close-pair re-evaluation active)",
                  "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                  "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / 2 = dense TF32 rate of the same pipe"

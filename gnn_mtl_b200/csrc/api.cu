@@ -8,6 +8,7 @@ thread_local int t_last_cuda_error = 0;
 extern int g_tune_unroll, g_tune_warps, g_tune_hints, g_tune_spmm_persist, g_tune_spmm_slab, g_tune_spmm_bulk, g_tune_spmm_dynamic;                       // spmm.cu
 extern int g_tune_persistent, g_tune_resident, g_tune_onchip, g_tune_scaling, g_tune_tile2d;     // sinkhorn_dense.cu
 extern int g_tune_absorb_milli, g_tune_force_fallback;
+extern int g_tune_tc_pair;                                                                        // sinkhorn_tc.cu
 extern int g_tune_gemm_pair;                                                                      // gemm_nt_raw.cu
 extern int g_tune_l1_filter;                                                                      // eval_l1.cu
 int sinkhorn_redo_count();
@@ -61,6 +62,7 @@ int eg_debug_set(int key, int value) {
     case 16: eg::g_tune_spmm_bulk = value; break;
     case 17: eg::g_tune_spmm_dynamic = value; break;
     case 18: eg::g_tune_gemm_pair = value; break;
+    case 19: eg::g_tune_tc_pair = value; break;
     default: return EG_ERR_INVALID;
   }
   return EG_OK;

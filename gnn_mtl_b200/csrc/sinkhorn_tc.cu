@@ -19,11 +19,16 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace eg {
+
+int g_tune_tc_pair = 1;          // knob 19: the tcgen05 kernels of this file on CTA pairs (cta_group::2; default) or single CTAs
+                                 // (same bits; fused half-sweep 30000^2 x 300: 2.24-2.27 ms against 2.32-2.36 ms,
+                                 //  [200k, 300] x [600 | 300, 300]^T 0.40 / 0.23 ms against 0.445 / 0.255 ms)
 
 namespace tc {
 
@@ -127,8 +132,15 @@ struct Params {
 //         registers (round-to-nearest) while the next block runs in the other buffer.  Error ~3e-7: the level of an
 //         fp32 SIMT product, which is what a ReLU-feeding product needs (layers/layers.py:32,61 feed F.relu).
 //         Column tile <= kFlushBN so that a thread's row of accumulators stays in registers.
+//
+// PAIR: the same kernel on pairs of CTAs (a 2-CTA cluster = the two SMs of a TPC, tcgen05.mma.cta_group::2).  The pair
+// computes a 256-row tile: every CTA loads its own 128 rows of A and HALF of the B tile (the tensor cores exchange the
+// halves), which takes the operand fetch + TMA fill of a 128 x 256 x 8 MMA from 160 cycles of the shared-memory port
+// (more than its 128 cycles of math: the single-CTA kernel is bound by that port) to 107.  Rank 0 issues the MMAs for
+// both SMs; TMA bytes of both CTAs count on its `full` barriers; tcgen05.commit multicasts `empty` / `tfull` to both;
+// the peer's epilogue warps arrive on the leader's `tempty`.  Rows, epilogue and outputs stay per CTA.
 constexpr int kFlushBN = 160;
-template <int MODE>
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -136,14 +148,19 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
               const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_base = smem;                                     // STAGES * 96 KB, 1024-aligned tiles
+  // a CTA of a pair stages half a B tile: 32 KB stages, six of them in the same 192 KB
+  constexpr int BTILE = PAIR ? B_TILE_BYTES / 2 : B_TILE_BYTES;
+  constexpr int STG = 2 * A_TILE_BYTES + 2 * BTILE;
+  constexpr int NST = PAIR ? (STAGES * STAGE_BYTES) / STG : STAGES;
+  static_assert(NST * STG <= STAGES * STAGE_BYTES && (2 * NST + 6) * 8 + 4 <= 256, "stage ring / barrier block out of its space");
+  uint8_t* stage_base = smem;                                     // NST stages of 1024-aligned tiles
   float2* colinfo = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES);   // [2][BN] (norm_b, pot_b)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2 * BN * 8);
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [3]  (MODE 3 rotates three accumulator buffers, the others two)
-  uint64_t* tempty = bars + 2 * STAGES + 3;   // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint64_t* full = bars;                 // [NST]
+  uint64_t* empty = bars + NST;          // [NST]
+  uint64_t* tfull = bars + 2 * NST;      // [3]  (MODE 3 rotates three accumulator buffers, the others two)
+  uint64_t* tempty = bars + 2 * NST + 3;      // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.x * BM;
@@ -155,26 +172,40 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   // MODE 0/1: this CTA owns one row tile and walks its column tiles.  MODE 2 (GEMM) is persistent: the CTA walks
   // row tiles blockIdx.x, blockIdx.x + gridDim.x, ... and all column tiles of each, as one continuous pipeline
   // (a 3-tile CTA spent a third of its life in prologue and the un-overlapped last epilogue).
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
+  const bool leader = crank == 0;
   const int n_rtiles = (int)((p.nA + BM - 1) / BM);
-  const int my_rtiles = GEMM ? (n_rtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  // persistent GEMM: CTAs (pairs) walk row tiles (256-row pair tiles) blockIdx.x, + gridDim.x, ...
+  const int n_walk = PAIR ? (n_rtiles + 1) / 2 : n_rtiles;
+  const int walkers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x, walker = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int my_rtiles = GEMM ? (n_walk - walker + walkers - 1) / walkers : 1;
   const int n_tiles = GEMM ? my_rtiles * n_btiles : max(t_end - t_begin, 0);
   auto tile_i0 = [&](int t) -> int64_t {
-    return GEMM ? ((int64_t)blockIdx.x + (int64_t)(t / n_btiles) * gridDim.x) * BM : i0;
+    if (!GEMM) return i0;
+    const int64_t w = (int64_t)walker + (int64_t)(t / n_btiles) * walkers;
+    return PAIR ? (2 * w + crank) * BM : w * BM;
   };
   auto tile_j0 = [&](int t) -> int { return GEMM ? (t % n_btiles) * bn : (t_begin + t) * BN; };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 3; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 8 : 4); }   // epilogue warps (of both CTAs)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation is a warp-wide instruction; this warp also frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync();          // both CTAs' barriers and TMEM exist before any cross-CTA signal
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -187,7 +218,23 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const int ti0 = (int)tile_i0(t);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = stage_base + s * STAGE_BYTES;
+          uint8_t* st = stage_base + s * STG;
+          if (PAIR) {
+            // own 128 rows of A, own half (bn / 2 rows) of B; all bytes of both CTAs count on the leader's barrier
+            if (leader) mbar_expect_tx(&full[s], 4 * A_TILE_BYTES + 2 * bn * BK * 4);
+            const int jh = j0 + (int)crank * (bn / 2);
+            if (!GEMM || kb < p.kb_split) {
+              tma_load_2d_pair(st, &map_a_hi, &full[s], kb * BK, ti0);
+              tma_load_2d_pair(st + A_TILE_BYTES, &map_a_lo, &full[s], kb * BK, ti0);
+            } else {
+              tma_load_2d_pair(st, &map_a2_hi, &full[s], (kb - p.kb_split) * BK, ti0);
+              tma_load_2d_pair(st + A_TILE_BYTES, &map_a2_lo, &full[s], (kb - p.kb_split) * BK, ti0);
+            }
+            tma_load_2d_pair(st + 2 * A_TILE_BYTES, &map_b_hi, &full[s], kb * BK, jh);
+            tma_load_2d_pair(st + 2 * A_TILE_BYTES + BTILE, &map_b_lo, &full[s], kb * BK, jh);
+            if (++s == NST) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[s], 2 * A_TILE_BYTES + 2 * bn * BK * 4);   // the B boxes are bn rows tall
           if (!GEMM || kb < p.kb_split) {
             tma_load_2d(st, &map_a_hi, &full[s], kb * BK, ti0);
@@ -197,16 +244,16 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             tma_load_2d(st + A_TILE_BYTES, &map_a2_lo, &full[s], (kb - p.kb_split) * BK, ti0);
           }
           tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full[s], kb * BK, j0);
-          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[s], kb * BK, j0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          tma_load_2d(st + 2 * A_TILE_BYTES + BTILE, &map_b_lo, &full[s], kb * BK, j0);
+          if (++s == NST) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues (elect_one) ==========
-    {
+    if (!PAIR || leader) {
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t idesc = make_idesc(BM, bn);
+      const uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, bn);
       int s = 0; uint32_t ph = 0;
       uint32_t chain = 0;                                  // MODE 3: accumulation chains issued so far
       for (int t = 0; t < n_tiles; ++t) {
@@ -226,11 +273,11 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           }
           mbar_wait(&full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st = smem_u32(stage_base + s * STAGE_BYTES);
+          const uint32_t st = smem_u32(stage_base + s * STG);
           const uint64_t a_hi = make_smem_desc(st);
           const uint64_t a_lo = make_smem_desc(st + A_TILE_BYTES);
           const uint64_t b_hi = make_smem_desc(st + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          const uint64_t b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + BTILE);
           // the last k-block may be partly past d_pad (TMA zero-fills it): skip those k-steps
           const int k_steps = min(BK / UK, (p.d_pad - kb * BK) / UK);
           if (elect_one()) {
@@ -238,19 +285,31 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             for (int k = 0; k < BK / UK; ++k) {
               if (k >= k_steps) break;
               const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);   // 32 B per k-step, in 16-byte units
-              umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, MODE == 3 ? (uint32_t)(k != 0) : (uint32_t)((kb | k) != 0));
-              umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
-              umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
+              const uint32_t acc0 = MODE == 3 ? (uint32_t)(k != 0) : (uint32_t)((kb | k) != 0);
+              if (PAIR) {
+                umma_tf32_pair(tmem_d, a_hi + koff, b_hi + koff, idesc, acc0);
+                umma_tf32_pair(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+                umma_tf32_pair(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
+              } else {
+                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, acc0);
+                umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1);
+              }
             }
-            umma_commit(&empty[s]);                           // smem stage reusable once these MMAs retire
-            if (MODE == 3) umma_commit(&tfull[buf]);          // chain complete: the epilogue folds it
+            if (PAIR) {
+              umma_commit_pair(&empty[s]);                    // frees the stage in both CTAs
+              if (MODE == 3) umma_commit_pair(&tfull[buf]);
+            } else {
+              umma_commit(&empty[s]);                         // smem stage reusable once these MMAs retire
+              if (MODE == 3) umma_commit(&tfull[buf]);        // chain complete: the epilogue folds it
+            }
           }
           __syncwarp();
           if (MODE == 3) ++chain;
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == NST) { s = 0; ph ^= 1; }
         }
         if (MODE != 3) {
-          if (elect_one()) umma_commit(&tfull[buf]);          // accumulator complete
+          if (elect_one()) { if (PAIR) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]); }   // accumulator complete
           __syncwarp();
         }
       }
@@ -309,7 +368,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[cb]);
+          if (lane == 0) { if (PAIR && !leader) arrive_on_leader(&tempty[cb]); else mbar_arrive(&tempty[cb]); }
         }
         if (trow < p.nA) {
 #pragma unroll
@@ -436,7 +495,7 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       // release the accumulator buffer: all tcgen05.ld of this warp have completed (wait::ld above)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) { if (PAIR && !leader) arrive_on_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
     }
     if (MODE == 0) {
       if (row < p.nA) {
@@ -452,10 +511,38 @@ lse_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   // ---- teardown: everyone done with TMEM before the owner frees it ----
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
+  if (PAIR) {
+    cluster_sync();                  // no remote arrive, multicast commit or pair MMA may still target a CTA that left
+    if (warp == 1)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+  } else if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
+}
+
+// One launch path for every instantiation: opt-in shared memory once per device, 2-CTA clusters for PAIR.
+template <int MODE, bool PAIR>
+static int launch_tc(dim3 grid, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+                     const CUtensorMap& mb_lo, const CUtensorMap& ma2_hi, const CUtensorMap& ma2_lo, const Params& p,
+                     cudaStream_t s) {
+  static PerDeviceOnce once;
+  EG_SET_SMEM_ONCE(once, EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      SMEM_BYTES)));
+  if (!PAIR) {
+    lse_tc_kernel<MODE, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma2_hi, ma2_lo, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EG_CUDA(cudaLaunchKernelEx(&cfg, lse_tc_kernel<MODE, true>, ma_hi, ma_lo, mb_hi, mb_lo, ma2_hi, ma2_lo, p));
+  }
+  EG_LAUNCHED();
+  return EG_OK;
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -530,6 +617,10 @@ struct Launch {
   Params p;
   int splits;
 };
+static bool use_pair() {
+  static const int env = [] { const char* e = getenv("EG_TC_PAIR"); return e ? atoi(e) : -1; }();   // measurement override
+  return (env >= 0 ? env : g_tune_tc_pair) != 0;
+}
 static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const float* normA, const float* normB,
                    float inv_reg, const float* pot_in, const float* A_hi, const float* A_lo, const float* B_hi,
                    const float* B_lo, const float* A_raw, const float* B_raw) {
@@ -541,8 +632,9 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
   int rc;
   if ((rc = make_map(&L->ma_hi, A_hi, nA, d_pad, BM))) return rc;
   if ((rc = make_map(&L->ma_lo, A_lo, nA, d_pad, BM))) return rc;
-  if ((rc = make_map(&L->mb_hi, B_hi, nB, d_pad, BN))) return rc;
-  if ((rc = make_map(&L->mb_lo, B_lo, nB, d_pad, BN))) return rc;
+  const int b_box = use_pair() ? BN / 2 : BN;               // a CTA of a pair stages half of the B tile
+  if ((rc = make_map(&L->mb_hi, B_hi, nB, d_pad, b_box))) return rc;
+  if ((rc = make_map(&L->mb_lo, B_lo, nB, d_pad, b_box))) return rc;
   L->ma2_hi = L->ma_hi;
   L->ma2_lo = L->ma_lo;
   Params& p = L->p;
@@ -551,11 +643,6 @@ static int prepare(Launch* L, int cost, int64_t nA, int64_t nB, int d, const flo
   p.normA = normA; p.normB = normB; p.pot_in = pot_in;
   p.A_raw = A_raw; p.B_raw = B_raw; p.d = d;
   pick_grid(nA, nB, &L->splits, &p.tiles_per_split);
-  static PerDeviceOnce attr_once;
-  EG_SET_SMEM_ONCE(attr_once,
-                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   return EG_OK;
 }
 }  // namespace tc
@@ -572,9 +659,11 @@ int lse_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, co
   if (ws_bytes < 2 * half) return EG_ERR_WORKSPACE;
   L.p.part_m = reinterpret_cast<float*>(ws);
   L.p.part_s = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + half);
-  dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);
-  lse_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
-  EG_LAUNCHED();
+  // pairs: an even number of row tiles (a tile past nA reads zeros and writes nothing)
+  dim3 grid((unsigned)(use_pair() ? 2 * ceil_div(nA, 2 * BM) : ceil_div(nA, BM)), (unsigned)L.splits);
+  rc = use_pair() ? launch_tc<0, true>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s)
+                  : launch_tc<0, false>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s);
+  if (rc) return rc;
   lse_combine_tc_kernel<<<(unsigned)ceil_div(nA, 256), 256, 0, s>>>(L.p.part_m, L.p.part_s, L.splits, nA, logw,
                                                                     pot_out, lse_out);
   EG_LAUNCHED();
@@ -591,10 +680,9 @@ int plan_fused_tc(int cost, int64_t nA, int64_t nB, int d, const float* normA, c
   int rc = prepare(&L, cost, nA, nB, d, normA, normB, inv_reg, g, A_hi, A_lo, B_hi, B_lo, A_raw, B_raw);
   if (rc) return rc;
   L.p.pot_a = f; L.p.loss = loss; L.p.row_sum = row_sum;
-  dim3 grid((unsigned)ceil_div(nA, BM), (unsigned)L.splits);
-  lse_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
-  EG_LAUNCHED();
-  return EG_OK;
+  dim3 grid((unsigned)(use_pair() ? 2 * ceil_div(nA, 2 * BM) : ceil_div(nA, BM)), (unsigned)L.splits);
+  return use_pair() ? launch_tc<1, true>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s)
+                    : launch_tc<1, false>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s);
 }
 
 
@@ -622,29 +710,27 @@ int gemm_nt_tc(const float* A1_hi, const float* A1_lo, int k1p, const float* A2_
   }
   // column tile: as few tiles as BN = 256 allows, each just wide enough (multiple of 16): n = 300 -> 2 x 160, not 2 x 256
   // (flush: short accumulation chains folded in registers, MODE 3 — the tile is capped so a row of sums fits)
+  const bool pair = use_pair();
   const int64_t bn_cap = flush ? kFlushBN : BN;
   const int64_t n_ct = ceil_div(n, bn_cap);
-  const int bn = (int)std::min<int64_t>(bn_cap, ceil_div(ceil_div(n, n_ct), (int64_t)16) * 16);
-  if ((rc = make_map(&L.mb_hi, B_hi, n, kp, bn))) return rc;
-  if ((rc = make_map(&L.mb_lo, B_lo, n, kp, bn))) return rc;
+  const int64_t gran = pair ? 32 : 16;                      // UMMA N granularity: 16 at M = 128, 32 for the 256-row pair MMA
+  const int bn = (int)std::min<int64_t>(bn_cap, ceil_div(ceil_div(n, n_ct), gran) * gran);
+  if ((rc = make_map(&L.mb_hi, B_hi, n, kp, pair ? bn / 2 : bn))) return rc;
+  if ((rc = make_map(&L.mb_lo, B_lo, n, kp, pair ? bn / 2 : bn))) return rc;
   Params& p = L.p;
   p = Params{};
   p.nA = m; p.nB = n; p.k_blocks = kp / BK; p.d_pad = kp; p.kb_split = k1p / BK;
   p.pot_in = bias; p.out1 = out1; p.out2 = out2; p.ld1 = ld1; p.ld2 = ld2; p.n1 = n1;
   p.bn = bn;
   p.tiles_per_split = (int)ceil_div(n, (int64_t)bn);
-  static PerDeviceOnce attr_once2, attr_once3;
-  EG_SET_SMEM_ONCE(attr_once2,
-                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
-  EG_SET_SMEM_ONCE(attr_once3,
-                   EG_CUDA(cudaFuncSetAttribute(lse_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
-  dim3 grid((unsigned)std::min<int64_t>(ceil_div(m, BM), kNumSMs), 1);    // persistent over row tiles
+  // persistent over row tiles (256-row tiles for pairs)
+  dim3 grid(pair ? 2u * (unsigned)std::min<int64_t>(ceil_div(m, 2 * BM), kNumSMs / 2)
+                 : (unsigned)std::min<int64_t>(ceil_div(m, BM), kNumSMs), 1);
   if (flush)
-    lse_tc_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
-  else
-    lse_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p);
-  EG_LAUNCHED();
-  return EG_OK;
+    return pair ? launch_tc<3, true>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s)
+                : launch_tc<3, false>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s);
+  return pair ? launch_tc<2, true>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s)
+              : launch_tc<2, false>(grid, L.ma_hi, L.ma_lo, L.mb_hi, L.mb_lo, L.ma2_hi, L.ma2_lo, L.p, s);
 }
 
 }  // namespace eg

@@ -638,6 +638,39 @@ def test_epilogue_bwd_float4_and_scalar_paths(shape, act_relu, gated, dev):
         assert torch.allclose(dX, g * (1 - t), rtol=1e-5, atol=1e-7)
 
 
+def test_tcgen05_kernels_cta_pairs_match_single_cta(dev):
+    """The kernels of sinkhorn_tc.cu run on CTA pairs (tcgen05.mma.cta_group::2, debug knob 19 = 1, the default) or on
+    single CTAs (0): fused LSE half-sweep (utils/ot_loss.py:58-70 on the fly), plan statistics, the NT GEMM and its
+    short-chain variant give identical bits either way, on ragged shapes and odd row-tile counts."""
+    from gnn_mtl_b200 import _lib, ops
+    torch.manual_seed(11)
+    knob = _lib.lib.eg_debug_set
+    try:
+        for nA, nB in ((100, 300), (129, 257), (1000, 5000), (3001, 2999)):
+            X = torch.randn(nA, 300, device=dev) * 0.06
+            Y = torch.randn(nB, 300, device=dev) * 0.06
+            if nA > 3000:
+                Y[:nB] = X[:nB] + 0.006 * torch.randn(nB, 300, device=dev)      # close pairs: exact re-evaluation branch
+            pot = torch.randn(nB, device=dev)
+            got = []
+            for on in (0, 1):
+                knob(19, on)
+                A = ops.FusedOperand(X, _lib.COST_L2, _lib.ALGO_TCGEN05)
+                B = ops.FusedOperand(Y, _lib.COST_L2, _lib.ALGO_TCGEN05)
+                got.append(ops.lse_fused(A, B, _lib.COST_L2, 20.0, pot, None, _lib.ALGO_TCGEN05, want_lse=True)[1].clone())
+            assert torch.equal(got[0], got[1]), (nA, nB)
+            ref = torch.logsumexp(pot[None, :].double() - 20.0 * torch.cdist(X.double(), Y.double()), 1)
+            assert float((got[1].double() - ref).abs().max()) < 2e-4
+        for m, k, n in ((130, 52, 340), (1, 16, 4), (128 * 149 + 5, 300, 600)):
+            a = torch.randn(m, k, device=dev); w = torch.randn(n, k, device=dev) * 0.1; b = torch.randn(n, device=dev)
+            for chained in (False, True):
+                knob(19, 0); r0 = ops.gemm_nt([a], w, b, chained=chained)
+                knob(19, 1); r1 = ops.gemm_nt([a], w, b, chained=chained)
+                assert torch.equal(r0, r1), (m, k, n, chained)
+    finally:
+        knob(19, 1)
+
+
 def test_margin_loss_golden_and_scale(golden_dir, dev):
     """Fused gather + L1 + hinge loss (models/models_ea.py:103-123): value and gradient."""
     from oracle import ea_oracle as orc
