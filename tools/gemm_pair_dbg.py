@@ -1,3 +1,7 @@
+"""Which rows of the CTA-pair raw-operand GEMM differ from the single-SM kernel, and why: for every wrong row the 160
+wrong outputs are solved (least squares per k-block) for the 16 A values that would produce them, and those values are
+searched for in A — this is how the early release of the raw A stage was identified (the stale values were the same
+row's k-block ten stages ahead = the ring depth)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
