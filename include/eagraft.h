@@ -63,6 +63,7 @@ void eg_launch_count_reset(void);
  *     17 persistent SpMM (knob 6) hands out rows through an atomic counter on/off,
  *     18 eg_gemm_nt_3xtf32_raw on CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles; default on) / single-SM kernel,
  *     19 the fused Sinkhorn / plan / split-operand NT GEMM kernels (tcgen05) on CTA pairs (default on) / single CTAs
+ *        (EG_TC_PAIR=0|1 in the environment overrides knob 19 for whole-process measurements)
  *   query (value ignored): 8 scaling-domain solves redone in the log domain so far, 9 fold steps so far
  * Queries 8/9 read device counters and synchronise the device. */
 int eg_debug_set(int key, int value);
