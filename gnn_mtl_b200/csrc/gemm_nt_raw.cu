@@ -21,11 +21,16 @@
 // epilogue, warps 8-11 = A converters (TMEM lane quadrant = warp % 4 for both).  TMEM: two accumulators of <= 176
 // columns + 5 A stages of 32 columns = 512.  Persistent over row tiles like the split-operand kernel.
 //
-// Measured (tools/gemm_raw_check.py, tools/gemm_raw_dbg.py; [200k, 300] operands): per k-block the issuing thread waits
-// 210 cycles for a ready stage and spends 536 in the (queue-blocked) issue of its six MMAs, i.e. the tensor pipe is busy
-// 64-72 % of the cycles; 0.248 ms at n = 300 (split-operand kernel 0.254 + 0.11 ms of split launch), dx (K = 2 x 300)
-// 0.459 ms (0.468 + 0.11).  At n = 600 the 176-column cap costs a fourth column tile (0.475 vs 0.438 ms): that
-// shape stays on the split-operand kernel.
+// Measured (tools/gemm_raw_check.py, tools/gemm_raw_dbg.py; [200k, 300] operands): 0.448 / 0.235 ms at n = 600 / 300, dx
+// (K = 2 x 300) 0.42 ms (split-operand kernel 0.434 / 0.251 + 0.11 ms of split launch per operand).  The "536 cycles of
+// queue-blocked issue" that the timers of the first versions showed were not the tensor pipe: the issuing loop ran
+// under `if (lane == 0)`, where every tcgen05.mma gets a register-broadcast loop around it (~45 cycles each; see
+// elect_one in tc_common.cuh).  With the warp-uniform issuer the six MMAs issue in ~225 cycles and the kernel is bound
+// by the shared-memory port (B pair + converter reads); the CTA-pair kernel (gemm_nt_raw2.cu) halves the B bytes per SM
+// and is the default behind eg_gemm_nt_3xtf32_raw — this one stays selectable (debug knob 18 = 0).
+//
+// The raw stage is released BEHIND the tensor-memory stores that consume the loaded registers: an arrive placed right
+// after the loads can overtake them (nothing makes it wait for load data) and the TMA refill then races the read.
 #include <cuda.h>
 
 #include <algorithm>
@@ -59,7 +64,7 @@ struct Params {
   int64_t m, n;
   int k1, k2;              // K extents of the two A operands (k2 = 0: one operand)
   int kb1, k_blocks;       // k-blocks of A1, total
-  int bn;                  // columns per tile (multiple of 16, <= 208)
+  int bn;                  // columns per tile (multiple of 16, <= BNMAX)
   const float* bias;       // [n] or null
   float* out1; float* out2;
   int64_t ld1, ld2, n1;
@@ -123,7 +128,7 @@ gemm_nt_raw_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;                                     // RA x 8 KB raw A stages
-  uint8_t* b_base = smem + RA * A_BYTES;                      // SB x 26 KB B pair stages (1024-aligned: RA * 8 KB)
+  uint8_t* b_base = smem + RA * A_BYTES;                      // SB B-pair stages (1024-aligned: RA * 8 KB in front)
   float* bias_s = reinterpret_cast<float*>(b_base + SB * B_STAGE);   // [2][BNMAX]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + 2 * BNMAX * 4);
   uint64_t* full_a = bars;                      // [RA]  TMA bytes of a raw A stage landed

@@ -116,7 +116,7 @@ gemm_nt_raw2_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_con
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;                                     // RA x 8 KB raw A stages
-  uint8_t* b_base = smem + RA * A_BYTES;                      // SB x 26 KB B pair stages (1024-aligned: RA * 8 KB)
+  uint8_t* b_base = smem + RA * A_BYTES;                      // SB B-pair stages (1024-aligned: RA * 8 KB in front)
   float* bias_s = reinterpret_cast<float*>(b_base + SB * B_STAGE);   // [2][BNMAX]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + 2 * BNMAX * 4);
   uint64_t* full_a = bars;                      // [RA]  TMA bytes of a raw A stage landed
