@@ -5,6 +5,8 @@ UEAModel.generate_pairs :143-167, generate_neg :169-183, get_loss_wassertein
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -14,6 +16,22 @@ from ..utils.eval_utils import get_hits
 from ..utils.ot_loss import sinkhorn
 from .decoders import model2decoder
 from .encoders import model2encoder
+
+
+# The Sinkhorn solve of get_loss_wassertein feeds nothing downstream (the plan is computed and then not used,
+# models_ea.py:221-222), so nothing in the backward pass or the optimizer step waits for it: it runs on a side stream
+# next to them and is joined at the end of the step (join_pending_solve).  The solve is latency-bound and leaves most
+# issue slots and all of the HBM bandwidth idle; the streaming kernels of the backward pass fill them.
+# EG_SINKHORN_OVERLAP=0 keeps everything on the caller's stream.
+OVERLAP_SINKHORN = os.environ.get("EG_SINKHORN_OVERLAP", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
 
 
 class BaseModel(nn.Module):
@@ -136,9 +154,28 @@ class UEAModel(BaseModel):
         Y = outputs[sample[1]]
         a, b = torch.ones(bsz, device=dev), torch.ones(bsz, device=dev)
         M = torch.cdist(X, Y, p=2)
-        T, _ = sinkhorn(a, b, M.detach(), reg=0.01, numItermax=numItermax, stopThr=stopThr, return_plan=False)
+        self.join_pending_solve()
+        if OVERLAP_SINKHORN and M.is_cuda and stopThr < 0:
+            # (with a stop rule the solver reads the marginal error back on the host: nothing to overlap)
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            Md = M.detach()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                sinkhorn(a, b, Md, reg=0.01, numItermax=numItermax, stopThr=stopThr, return_plan=False)
+            for t in (Md, a, b):
+                t.record_stream(side)
+            self._pending_solve = side
+        else:
+            T, _ = sinkhorn(a, b, M.detach(), reg=0.01, numItermax=numItermax, stopThr=stopThr, return_plan=False)
         # newT = one-hot(argmax(zeros)) = column 0 of every row (reference :221-222)
         return torch.sum(M[:, 0].to(torch.float64))
+
+    def join_pending_solve(self):
+        """Make the caller's stream wait for a Sinkhorn solve still running on the side stream (end of a step)."""
+        side = getattr(self, "_pending_solve", None)
+        if side is not None:
+            torch.cuda.current_stream(side.device).wait_stream(side)
+            self._pending_solve = None
 
 
 def _gw_loss(self, outputs, data, bsz, *, max_iter=1000, epsilon=0.01, sample=None):

@@ -38,6 +38,7 @@ def train_unsup_ea(args, data=None, log=print):
             loss = model.get_loss_wassertein(outputs, data, args.batch_size)
             loss.backward()
             optimizer.step()
+            model.join_pending_solve()
         scheduler.step()
         if (epoch + 1) % args.eval_freq == 0:
             model.eval()

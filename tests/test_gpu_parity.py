@@ -671,6 +671,40 @@ def test_tcgen05_kernels_cta_pairs_match_single_cta(dev):
         knob(19, 1)
 
 
+def test_wasserstein_loss_solve_on_side_stream(golden_dir, dev):
+    """get_loss_wassertein (models/models_ea.py:206-224) with every sweep forced (stopThr < 0) runs its Sinkhorn solve
+    on a side stream next to the caller's backward pass; loss and gradient are those of the serialised call, the solve
+    is joined by join_pending_solve(), and with a stop rule (host read-back) the call stays on the caller's stream."""
+    from gnn_mtl_b200.models import models_ea
+    g = _load(golden_dir, "sinkhorn.npz")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])[:40]
+
+    class _U(models_ea.UEAModel):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+    data = {"e1": 40, "e2": 40, "index1": np.arange(40), "index2": np.arange(40) + 40}
+    sample = (torch.arange(40, device=dev), torch.arange(40, device=dev) + 40)
+    res = []
+    saved = models_ea.OVERLAP_SINKHORN
+    try:
+        for ov in (False, True):
+            models_ea.OVERLAP_SINKHORN = ov
+            m = _U()
+            out = torch.cat([X, Y]).to(dev).requires_grad_(True)
+            loss = m.get_loss_wassertein(out, data, 40, numItermax=200, stopThr=-1.0, sample=sample)
+            assert (getattr(m, "_pending_solve", None) is not None) == ov
+            loss.backward()
+            m.join_pending_solve()
+            assert getattr(m, "_pending_solve", None) is None
+            torch.cuda.synchronize()
+            res.append((float(loss), out.grad.clone()))
+            loss2 = m.get_loss_wassertein(out, data, 40, numItermax=50, sample=sample)       # stop rule: serialised
+            assert getattr(m, "_pending_solve", None) is None and abs(float(loss2) - float(loss)) < 1e-9
+    finally:
+        models_ea.OVERLAP_SINKHORN = saved
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+
+
 def test_margin_loss_golden_and_scale(golden_dir, dev):
     """Fused gather + L1 + hinge loss (models/models_ea.py:103-123): value and gradient."""
     from oracle import ea_oracle as orc
