@@ -496,7 +496,8 @@ def run_ours(args):
     opt = torch.optim.Adam(params, lr=1e-3)
     # N > 1: every parameter's gradient is all-reduced from its autograd hook while the rest of the backward runs
     # (EG_BENCH_FLAT_ALLREDUCE=1: one flat all-reduce after backward instead — measurement switch)
-    flat_sync = world > 1 and os.environ.get("EG_BENCH_FLAT_ALLREDUCE") == "1"
+    from gnn_mtl_b200.models import models_ea as _mea0
+    flat_sync = world > 1 and (os.environ.get("EG_BENCH_FLAT_ALLREDUCE") == "1" or _mea0.OVERLAP_SINKHORN)
     grad_sync = parallel.OverlappedGradSync(params) if (world > 1 and not flat_sync) else None
     data = {"e1": kg["e1"], "e2": kg["e2"], "index1": np.arange(kg["e1"]), "index2": np.arange(kg["e2"]) + kg["e1"]}
     bsz, iters = args.bsz, args.sinkhorn_iters
@@ -520,6 +521,10 @@ def run_ours(args):
         if grad_sync is not None:
             grad_sync.finish()
         elif flat_sync:
+            # with the Sinkhorn solve on a side stream the gradient exchange waits for it: an NCCL kernel that has to
+            # squeeze in next to a solve holding 120 SMs on one rank stalls its peer on the other (measured at
+            # N = 2: 23.7 ms per step with hook-driven all-reduces under the solve, against 12.5 ms at N = 1)
+            model.join_pending_solve()
             parallel.allreduce_grads(params)
         opt.step()
         model.join_pending_solve()        # the Sinkhorn solve of this step (side stream) belongs to this step

@@ -84,7 +84,11 @@ class OverlappedGradSync:
     gradients travel while the earlier layers are still being differentiated); ``finish()`` waits for the
     outstanding reductions and divides by the world size — call it between ``loss.backward()`` and
     ``optimizer.step()``.  Replaces the flat, synchronous ``allreduce_grads`` after backward (the 1→8 GPU curve of
-    round 1 lost its last 2.6 % there)."""
+    round 1 lost its last 2.6 % there).
+
+    Not together with a Sinkhorn solve running on a side stream (models_ea.OVERLAP_SINKHORN): an NCCL kernel that has
+    to squeeze in next to a solve holding 120 SMs on one rank stalls its peer on the other rank (measured at N = 2:
+    23.7 ms per step against 12.6 ms with ``join_pending_solve()`` + the flat ``allreduce_grads`` after backward)."""
 
     def __init__(self, params, group=None):
         self.group = group
