@@ -34,6 +34,34 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
+# The as-shipped objective is sum_i M[i, 0] with M = cdist(X, Y) (models_ea.py:218-224: the one-hot comes from the argmax
+# of a zero tensor).  Its gradient is known in closed form — d M[i,0] / d X_i = (X_i - Y_0) / M[i,0], and Y_0 gets minus
+# the sum — so the backward pass does not have to push a one-hot [bsz, bsz] gradient through cdist's matmul
+# formulation (two 3000 x 3000 x 300 products and a dozen element-wise passes for 3000 non-zero entries).  The value is
+# still read from the same cdist matrix the Sinkhorn solve gets.  EG_COL0_GRAD=0 restores autograd through cdist.
+CLOSED_FORM_COL0_GRAD = os.environ.get("EG_COL0_GRAD", "1") != "0"
+
+
+class _Column0Loss(torch.autograd.Function):
+    """sum_i M[i, 0] as a function of X, Y with m0 = M[:, 0] = ||X_i - Y_0||_2 given (cdist's own values)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, m0):
+        ctx.save_for_backward(X, Y[0], m0)
+        ctx.y_shape = Y.shape
+        return torch.sum(m0.to(torch.float64))
+
+    @staticmethod
+    def backward(ctx, g):
+        X, y0, m0 = ctx.saved_tensors
+        # cdist's backward divides by the distance too (and gives 0 at an exact zero distance)
+        w = torch.where(m0 > 0, g.to(m0.dtype) / m0, torch.zeros_like(m0)).unsqueeze(1)
+        dX = (X - y0) * w
+        dY = torch.zeros(ctx.y_shape, dtype=X.dtype, device=X.device)
+        dY[0] = -dX.sum(0)
+        return dX, dY, None
+
+
 class BaseModel(nn.Module):
     def __init__(self, args):
         super(BaseModel, self).__init__()
@@ -153,7 +181,12 @@ class UEAModel(BaseModel):
         X = outputs[sample[0]]
         Y = outputs[sample[1]]
         a, b = torch.ones(bsz, device=dev), torch.ones(bsz, device=dev)
-        M = torch.cdist(X, Y, p=2)
+        closed_form = CLOSED_FORM_COL0_GRAD and X.is_cuda
+        if closed_form:
+            with torch.no_grad():
+                M = torch.cdist(X, Y, p=2)
+        else:
+            M = torch.cdist(X, Y, p=2)
         self.join_pending_solve()
         if OVERLAP_SINKHORN and M.is_cuda and stopThr < 0:
             # (with a stop rule the solver reads the marginal error back on the host: nothing to overlap)
@@ -168,6 +201,8 @@ class UEAModel(BaseModel):
         else:
             T, _ = sinkhorn(a, b, M.detach(), reg=0.01, numItermax=numItermax, stopThr=stopThr, return_plan=False)
         # newT = one-hot(argmax(zeros)) = column 0 of every row (reference :221-222)
+        if closed_form:
+            return _Column0Loss.apply(X, Y, M[:, 0].contiguous())
         return torch.sum(M[:, 0].to(torch.float64))
 
     def join_pending_solve(self):

@@ -90,3 +90,22 @@ def test_synth_shapes():
     assert kg["triples"][:, [0, 2]].max() < 610
     kg2 = make_kg_pair("tiny", dim=16)
     assert np.array_equal(kg["triples"], kg2["triples"]) and np.array_equal(kg["x"], kg2["x"])
+
+
+def test_column0_loss_closed_form_gradient_matches_autograd_through_cdist():
+    """models/models_ea.py:218-224 as shipped is sum_i cdist(X, Y)[i, 0]; the closed-form backward used by
+    get_loss_wassertein gives the gradient autograd derives through torch.cdist (fp64, CPU)."""
+    import torch
+    from gnn_mtl_b200.models.models_ea import _Column0Loss
+    torch.manual_seed(0)
+    X = torch.randn(50, 30, dtype=torch.float64, requires_grad=True)
+    Y = torch.randn(40, 30, dtype=torch.float64, requires_grad=True)
+    want_loss = torch.cdist(X, Y, p=2)[:, 0].sum()
+    want = torch.autograd.grad(want_loss, [X, Y])
+    with torch.no_grad():
+        m0 = torch.cdist(X, Y, p=2)[:, 0].contiguous()
+    got_loss = _Column0Loss.apply(X, Y, m0)
+    got = torch.autograd.grad(got_loss * 3.0, [X, Y])
+    assert float(want_loss.detach() - got_loss.detach()) == 0.0
+    assert float((3.0 * want[0] - got[0]).abs().max()) < 1e-12 and float((3.0 * want[1] - got[1]).abs().max()) < 1e-12
+    assert float(got[1][1:].abs().max()) == 0.0

@@ -703,6 +703,19 @@ def test_wasserstein_loss_solve_on_side_stream(golden_dir, dev):
     finally:
         models_ea.OVERLAP_SINKHORN = saved
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+    # closed-form gradient of sum_i M[i, 0] against autograd through torch.cdist: same loss bits, gradient to rounding
+    saved_cf = models_ea.CLOSED_FORM_COL0_GRAD
+    try:
+        models_ea.CLOSED_FORM_COL0_GRAD = False
+        m = _U()
+        out = torch.cat([X, Y]).to(dev).requires_grad_(True)
+        loss = m.get_loss_wassertein(out, data, 40, numItermax=200, stopThr=-1.0, sample=sample)
+        loss.backward()
+        m.join_pending_solve()
+    finally:
+        models_ea.CLOSED_FORM_COL0_GRAD = saved_cf
+    assert float(loss) == res[0][0]
+    assert float((out.grad - res[0][1]).abs().max()) <= 1e-5 * float(out.grad.abs().max())
 
 
 def test_margin_loss_golden_and_scale(golden_dir, dev):
