@@ -494,8 +494,10 @@ def run_ours(args):
     model = UEAModel(model_args(kg["n"], dev, local)).to(dev)
     params = list(model.parameters())
     opt = torch.optim.Adam(params, lr=1e-3)
-    # N > 1: every parameter's gradient is all-reduced from its autograd hook while the rest of the backward runs
-    # (EG_BENCH_FLAT_ALLREDUCE=1: one flat all-reduce after backward instead — measurement switch)
+    # N > 1: with the step's Sinkhorn solve on its side stream (the default) the gradients are exchanged in one flat
+    # all-reduce after backward, once the solve has joined; with the solve serialised (EG_SINKHORN_OVERLAP=0) every
+    # parameter's gradient is all-reduced from its autograd hook while the rest of the backward runs
+    # (EG_BENCH_FLAT_ALLREDUCE=1 forces the flat variant there too — measurement switch)
     from gnn_mtl_b200.models import models_ea as _mea0
     flat_sync = world > 1 and (os.environ.get("EG_BENCH_FLAT_ALLREDUCE") == "1" or _mea0.OVERLAP_SINKHORN)
     grad_sync = parallel.OverlappedGradSync(params) if (world > 1 and not flat_sync) else None
